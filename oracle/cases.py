@@ -1,0 +1,92 @@
+"""Parity cases shared by oracle/make_golden.py (reference side) and tests/ (CUDA side).
+
+TEST INFRASTRUCTURE ONLY.  A case names a lattice, a model and a seed; `build_case` expands it to the
+arguments of `SimpleUpdate`.  The five BASELINE.json configs appear at their full steady-state
+shapes (star D=2, "peps" D=8, TFI "peps" D=4, triangle spin-1 BLBQ D=4, 16x16 OBC D=6) next to the
+edge cases the reference's own tests exercise (bond growth, the chain's M>N branch, field terms,
+complex initial tensors, heterogeneous coordination).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DTS = [0.1, 0.01, 0.001, 0.0001, 0.00001]
+
+CASES = {
+    # ---- n sweeps at fixed dt from a seeded random network ("sweep" kind) ----
+    "star_D2": dict(kind="sweep", lattice="star", model="afh", d=2, virtual_dim=2, d_max=2, sweeps=4, seed=42),
+    "peps_D8": dict(kind="sweep", lattice="peps", model="afh", d=2, virtual_dim=8, d_max=8, sweeps=3, seed=0),
+    "tfi_D4": dict(kind="sweep", lattice="peps", model="tfi", h=-3.0, d=2, virtual_dim=4, d_max=4, sweeps=3, seed=3),
+    "blbq_D4": dict(kind="sweep", lattice="triangle", model="blbq", angle=0.3 * np.pi, d=3, virtual_dim=4, d_max=4,
+                    sweeps=2, seed=4),
+    "obc16_D6": dict(kind="sweep", lattice="obc:16x16", model="afh", d=2, virtual_dim=6, d_max=6, sweeps=2, seed=5),
+    "chain_growth": dict(kind="sweep", lattice="chain", model="afh", d=2, virtual_dim=2, d_max=10, sweeps=5, seed=6),
+    "peps_growth": dict(kind="sweep", lattice="peps", model="afh_field", h=0.3, field="x", d=2, virtual_dim=2,
+                        d_max=4, sweeps=4, seed=7),
+    "pyro_field": dict(kind="sweep", lattice="pyrochlore", model="afh_field", j=-1.0, h=0.1, field="z", d=2,
+                       virtual_dim=2, d_max=3, sweeps=2, seed=8),
+    "star_complex": dict(kind="sweep", lattice="star", model="afh_field", h=0.2, field="y", d=2, virtual_dim=3,
+                         d_max=3, sweeps=3, seed=9, complex_init=True),
+    "cube_D2": dict(kind="sweep", lattice="cube", model="afh", d=2, virtual_dim=2, d_max=2, sweeps=2, seed=10),
+    "obc4x3_D3": dict(kind="sweep", lattice="obc:4x3", model="afh", d=2, virtual_dim=3, d_max=3, sweeps=3, seed=11),
+    "kagome_spin1": dict(kind="sweep", lattice="kagome_3", model="afh", d=3, virtual_dim=3, d_max=3, sweeps=3,
+                         seed=12),
+    "pbc3_D2_dt0": dict(kind="sweep", lattice="pbc:3", model="afh", d=2, virtual_dim=2, d_max=2, sweeps=2, seed=13,
+                        dt=0.0),
+    # ---- whole SimpleUpdate.run() ("run" kind) ----
+    "run_star_D2": dict(kind="run", lattice="star", model="afh", d=2, virtual_dim=2, d_max=2, seed=42),
+    "run_tfi_D2_h4": dict(kind="run", lattice="peps", model="tfi_ref_test", h=-4.0, d=2, virtual_dim=2, d_max=2,
+                          seed=42),
+    "run_tfi_D4_h3": dict(kind="run", lattice="peps", model="tfi", h=-3.0, d=2, virtual_dim=4, d_max=4, seed=17),
+    "run_peps_D4_growth": dict(kind="run", lattice="peps", model="afh", d=2, virtual_dim=2, d_max=4, seed=42),
+}
+
+
+def _lattice(name, smc):
+    if name.startswith("obc:"):
+        h, w = name[4:].split("x")
+        return smc.rectangular_peps_obc(int(h), int(w))
+    if name.startswith("pbc:"):
+        return smc.square_peps_pbc(int(name[4:]))
+    return smc.infinite_structure_matrix_dict(name)
+
+
+def blbq_hamiltonian(angle, spin_ops):
+    """cos(a) sum_a S_a x S_a + sin(a) sum_ab (S_a S_b) x (S_a S_b)  ( = cos S.S + sin (S.S)^2 ),
+    the bilinear-biquadratic spin-1 model of notebooks/Triangular_..._simulation.ipynb:188-205."""
+    lin = sum(np.kron(s, s) for s in spin_ops)
+    quad = sum(np.kron(a @ b, a @ b) for a in spin_ops for b in spin_ops)
+    return np.cos(angle) * lin + np.sin(angle) * quad
+
+
+def build_case(name, smc=None, spin_operators=None):
+    """Expand CASES[name].  `smc` / `spin_operators` default to the reference's modules when they
+    are importable (make_golden.py) — tests pass the package's own, which are pinned separately."""
+    if smc is None:
+        import tnsu.structure_matrix_constructor as smc  # reference, only inside make_golden.py
+    if spin_operators is None:
+        from tnsu.math_objects import spin_operators
+    c = dict(CASES[name])
+    smat = _lattice(c["lattice"], smc)
+    m = smat.shape[1]
+    d = c["d"]
+    sx, sy, sz = spin_operators((d - 1) / 2.0)
+    px = np.array([[0, 1], [1, 0]])
+    pz = np.array([[1, 0], [0, -1]])
+    out = dict(c, smat=smat, hamiltonian=None, dt=c.get("dt", 0.1), dts=DTS, max_iterations=200, tol=1e-6)
+    model = c["model"]
+    if model == "afh":
+        out.update(j_ij=[1.0] * m, h_k=0.0, s_i=[sx, sy, sz], s_j=[sx, sy, sz], s_k=[])
+    elif model == "afh_field":
+        f = {"x": sx, "y": sy, "z": sz}[c["field"]]
+        out.update(j_ij=[c.get("j", 1.0)] * m, h_k=c["h"], s_i=[sx, sy, sz], s_j=[sx, sy, sz], s_k=[f])
+    elif model == "tfi":  # notebooks/Quantum_Ising_Model_Phase_Transition.ipynb:298-326
+        out.update(j_ij=[-1.0] * m, h_k=c["h"], s_i=[pz], s_j=[pz], s_k=[px])
+    elif model == "tfi_ref_test":  # examples.py:66-197 as called by tests/test_main.py:60-65
+        out.update(j_ij=[1.0] * m, h_k=c["h"], s_i=[pz], s_j=[pz], s_k=[px])
+    elif model == "blbq":
+        out.update(j_ij=[], h_k=0, s_i=[sx, sy, sz], s_j=[sx, sy, sz], s_k=[],
+                   hamiltonian=blbq_hamiltonian(c["angle"], [sx, sy, sz]))
+    else:
+        raise KeyError(model)
+    return out

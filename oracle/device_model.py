@@ -1,0 +1,164 @@
+"""numpy model of the ALGORITHM the CUDA kernels implement.  TEST INFRASTRUCTURE ONLY.
+
+The reference (and `tnsu_oracle.py`) use LAPACK RQ + gesdd.  The sm_100a kernels use a different,
+gauge-equivalent route ("Kernel math"):
+
+  * in-place Householder LQ on the rows of the absorbed bond matrix P (reflector k is left in row k),
+  * compact-WY form of the reflectors, so that P' = r~ . Q becomes one sync-free small GEMM
+        P' = [r~ 0] - (r~ . Y1 . T^H) . Y^H,
+  * one-sided (Hestenes) Jacobi SVD of theta with accumulated right vectors.
+
+This module states that route step by step in numpy with the same index conventions as
+`csrc/edge_update.cuh`, so the math can be checked against the oracle on the CPU
+(`tests/test_device_model.py`) before any GPU time is spent.  It is not a fallback: nothing in the
+product package imports it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from tnsu_oracle import edge_endpoints, tensor_legs
+
+
+def bond_matrix(tensor, weights, smat, t, ek):
+    """P[(s, x_k), c] = T[s, ...] * prod_{m != k} lam_m[x_m]; columns c enumerate the other legs in
+    memory order (any fixed order is admissible: Q never leaves the kernel)."""
+    edges, axes = tensor_legs(smat, t, ek)
+    a = int(smat[t, ek])
+    scaled = tensor.astype(complex) if np.iscomplexobj(tensor) else tensor.astype(float)
+    for e, ax in zip(edges, axes):
+        shape = [1] * tensor.ndim
+        shape[ax] = len(weights[e])
+        scaled = scaled * np.reshape(weights[e], shape)
+    moved = np.moveaxis(scaled, a, 1)
+    return np.reshape(moved, (moved.shape[0] * moved.shape[1], -1)), moved.shape
+
+
+def householder_lq_inplace(p):
+    """P (M x N) -> L (M x K), reflector rows Yh (K x N, row k = u_k^H, zero for c < k), tau (K).
+    P . H_0 ... H_{K-1} = [L 0],  H_k = I - tau_k u_k u_k^H.  Mirrors the kernel: one Gram-row
+    reduction g_i = sum_{c>k} P[i,c] conj(P[k,c]) over ALL rows per step (rows i<k give the
+    reflector inner products needed for the compact-WY T factor)."""
+    p = np.array(p)
+    m, n = p.shape
+    k_dim = min(m, n)
+    l_mat = np.zeros((m, k_dim), dtype=p.dtype)
+    tau = np.zeros(k_dim)
+    t_mat = np.zeros((k_dim, k_dim), dtype=p.dtype)  # upper triangular
+    for k in range(k_dim):
+        g = p[:, k + 1:] @ np.conj(p[k, k + 1:])  # one block reduction, M values
+        alpha = p[k, k]
+        norm2 = np.real(g[k]) + abs(alpha) ** 2
+        norm = np.sqrt(norm2)
+        if norm == 0.0:
+            tau[k] = 0.0
+            l_mat[k:, k] = 0.0
+            p[k, k] = 0.0
+            continue
+        absa = abs(alpha)
+        phase_c = (np.conj(alpha) / absa) if absa > 0 else 1.0  # conj(alpha)/|alpha|
+        # u_k (column vector): u[c] = conj(P[k,c]) for c>k, u[k] = conj(alpha) + phase_c*norm
+        uk_head = np.conj(alpha) + phase_c * norm
+        tau[k] = 1.0 / (norm * (norm + absa))
+        # z_i = u_i^H u_k for i<k :  tail + stored head  (P[i,k] = conj(u_i[k]) for i<k)
+        z = g[:k] + p[:k, k] * uk_head
+        # dots for rows i>k: p_i . u_k = g_i + P[i,k]*uk_head
+        w = tau[k] * (g[k + 1:] + p[k + 1:, k] * uk_head)
+        # update rows i>k: P[i,c] -= w_i * conj(u_k[c])
+        p[k + 1:, k + 1:] -= np.outer(w, p[k, k + 1:])
+        p[k + 1:, k] -= w * np.conj(uk_head)
+        l_mat[k, k] = -np.conj(phase_c) * norm  # = conj(beta'), beta' = -phase_c*norm
+        l_mat[k + 1:, k] = p[k + 1:, k]
+        p[k, k] = np.conj(uk_head)  # row k now stores u_k^H on c>=k
+        p[k, :k] = 0.0
+        # compact WY:  T[:k,k] = -tau_k T[:k,:k] z ;  T[k,k] = tau_k
+        t_mat[:k, k] = -tau[k] * (t_mat[:k, :k] @ z)
+        t_mat[k, k] = tau[k]
+    return l_mat, p[:k_dim, :], tau, t_mat
+
+
+def recompose(r_tilde, yh, t_mat):
+    """P' = r~ . Q with Q = [I_K 0] (I - Y T^H Y^H):  P' = [r~ 0] - (r~ Y1 T^H) Y^H."""
+    k_dim = yh.shape[0]
+    y1 = np.conj(yh[:, :k_dim]).T  # K x K, lower triangular: Y1[c,k] = u_k[c]
+    c_mat = r_tilde @ y1 @ np.conj(t_mat).T
+    out = -c_mat @ yh
+    out[:, :k_dim] += r_tilde
+    return out
+
+
+def jacobi_svd(a, tol=1e-15, max_sweeps=60):
+    """One-sided Jacobi on the columns of A (rows >= cols): A V = U diag(s).  Round-robin pair
+    order; rotation is the standard Hermitian 2x2 diagonalisation.  Returns u, s, vh sorted."""
+    a = np.array(a)
+    transposed = a.shape[0] < a.shape[1]
+    if transposed:
+        a = np.conj(a.T)
+    n_rows, n = a.shape
+    v = np.eye(n, dtype=a.dtype)
+    for _ in range(max_sweeps):
+        rotated = False
+        for p in range(n - 1):
+            for q in range(p + 1, n):
+                alpha = np.real(np.vdot(a[:, p], a[:, p]))
+                beta = np.real(np.vdot(a[:, q], a[:, q]))
+                gamma = np.vdot(a[:, p], a[:, q])  # a_p^H a_q
+                ag = abs(gamma)
+                if ag <= tol * np.sqrt(alpha * beta) or ag == 0.0:
+                    continue
+                rotated = True
+                zeta = (beta - alpha) / (2.0 * ag)
+                t = np.sign(zeta) / (abs(zeta) + np.sqrt(1.0 + zeta * zeta)) if zeta != 0 else 1.0
+                c = 1.0 / np.sqrt(1.0 + t * t)
+                s = c * t
+                ph = gamma / ag  # e^{i phi}
+                for mat in (a, v):
+                    cp_, cq_ = mat[:, p].copy(), mat[:, q].copy()
+                    mat[:, p] = c * cp_ - s * np.conj(ph) * cq_
+                    mat[:, q] = s * ph * cp_ + c * cq_
+        if not rotated:
+            break
+    sv = np.sqrt(np.real(np.sum(a * np.conj(a), axis=0)))
+    order = np.argsort(-sv, kind="stable")
+    sv = sv[order]
+    a = a[:, order]
+    v = v[:, order]
+    u = a / np.where(sv > 0, sv, 1.0)
+    if transposed:
+        return v, sv, np.conj(u.T)
+    return u, sv, np.conj(v.T)
+
+
+def edge_update(tensors, weights, smat, ek, gate, d_max):
+    """Same contract as tnsu_oracle.edge_update, computed the way the kernel does."""
+    ti, ai, tj, aj = edge_endpoints(smat, ek)
+    lam = weights[ek]
+    sides = []
+    for t in (ti, tj):
+        p, moved_shape = bond_matrix(tensors[t], weights, smat, t, ek)
+        l_mat, yh, tau, t_mat = householder_lq_inplace(p)
+        sides.append((l_mat, yh, t_mat, moved_shape))
+    (l_i, yh_i, t_i, sh_i), (l_j, yh_j, t_j, sh_j) = sides
+    d_i, d_j = sh_i[0], sh_j[0]
+    k_i, k_j = l_i.shape[1], l_j.shape[1]
+    dk = len(lam)
+    r_i = np.reshape(l_i, (d_i, dk, k_i))
+    r_j = np.reshape(l_j, (d_j, dk, k_j))
+    theta = np.einsum("ieq,e,jep,ijab->qabp", r_i, lam, r_j, gate)
+    u, s, vh = jacobi_svd(np.reshape(theta, (k_i * d_i, d_j * k_j)))
+    d_new = min(d_max, len(s)) if d_max is not None else len(s)
+    u, s, vh = u[:, :d_new], s[:d_new], vh[:d_new, :]
+    rt_i = np.reshape(np.transpose(np.reshape(u, (k_i, d_i, d_new)), (1, 2, 0)), (d_i * d_new, k_i))
+    rt_j = np.reshape(np.transpose(np.reshape(vh, (d_new, d_j, k_j)), (1, 0, 2)), (d_j * d_new, k_j))
+    for t, a, rt, yh, t_mat, sh in ((ti, ai, rt_i, yh_i, t_i, sh_i), (tj, aj, rt_j, yh_j, t_j, sh_j)):
+        p_new = recompose(rt, yh, t_mat)
+        new_shape = list(sh)
+        new_shape[1] = d_new
+        out = np.moveaxis(np.reshape(p_new, new_shape), 1, a)
+        edges, axes = tensor_legs(smat, t, ek)
+        for e, ax in zip(edges, axes):
+            shape = [1] * out.ndim
+            shape[ax] = len(weights[e])
+            out = out * np.reshape(1.0 / weights[e], shape)
+        tensors[t] = out / np.sqrt(np.real(np.sum(out * np.conj(out))))
+    weights[ek] = s / np.sum(s)
