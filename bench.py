@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — SU edge-updates/s at D=8 on the square-lattice ("peps" cell) spin-1/2 AFH model.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one Simple-Update sweep (8 edge updates: absorb, QR reduction, gate, truncated SVD,
+renormalise) over a batch of B independent random-init networks of BASELINE.json configs[1]
+(d=2, virtual_dim = d_max = 8, j_ij=1, h_k=0, dt=0.1, seed b for network b).  B is chosen so the state
+(B x 4 tensors x 8192 float64 = B x 256 KiB) is far larger than the 126 MB L2.
+
+  value  edge-updates/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks)
+  e2e    the same metric through the public API with host buffers: every step uploads the B networks from
+         pinned host memory, runs the sweep, evaluates energy_per_site and reads energies + weights back
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
+
+--impl reference times the reference's algorithm on the host cores (the numpy/scipy oracle port; the
+reference itself is pure Python and cannot travel to the GPU box), one process per core.
+"""
+import os
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")  # the reference's operating point is one BLAS thread
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tensor-networks-simple-update_b200"))
+
+METRIC = "SU edge-updates/s at D=8 square AFH"
+UNIT = "edge-updates/s"
+D, DIM, N_T, N_E = 2, 8, 4, 8  # physical dim, bond dim, tensors, edges of the "peps" cell
+WORKLOAD = "configs[1]: 2D square-lattice iPEPS ('peps' cell) spin-1/2 AFH, d=2, virtual_dim=d_max=8, dt=0.1"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def algorithmic_bytes_per_edge(scalar_bytes):
+    """read both site tensors once, write both once, read the weight vectors of all legs, write
+    one: 2*s*d*(D^z_i + D^z_j) + 8*(sum of leg dims)."""
+    return 2 * scalar_bytes * D * (DIM ** 4 + DIM ** 4) + 8 * (8 * DIM)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def seeded_networks(batch, first_seed=0):
+    """Host state exactly as TensorNetwork.__init__ draws it (legacy global numpy stream, seed b for network b)."""
+    import tnsu_b200 as tnsu
+
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    tensors = [np.empty((batch, D) + (DIM,) * 4) for _ in range(N_T)]
+    for b in range(batch):
+        np.random.seed(first_seed + b)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, spin_dim=D, virtual_dim=DIM)
+        for t in range(N_T):
+            tensors[t][b] = tn.tensors[t]
+    weights = np.full((batch, DIM), 1.0 / DIM)
+    return smat, tensors, weights
+
+
+def afh_operators():
+    import tnsu_b200 as tnsu
+    from scipy import linalg
+
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    ham = sum(np.kron(s, s) for s in (sx, sy, sz)).astype(complex)  # j_ij = 1, h_k = 0
+    return ham, linalg.expm(-0.1 * ham)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, budget_s, min_sweeps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tensor-networks-simple-update_b200"))
+    import tnsu_oracle as orc
+    from tnsu_b200 import smc
+
+    smat = smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = orc.spin_operators(0.5)
+    model = orc.Model([1.0] * N_E, 0.0, [sx, sy, sz], [sx, sy, sz], [])
+    np.random.seed(seed)
+    tensors, weights = orc.random_network(smat, D, DIM)
+    orc.sweep(tensors, weights, smat, model, 0.1, DIM)  # warm-up
+    t0 = time.perf_counter()
+    sweeps = 0
+    while sweeps < min_sweeps or time.perf_counter() - t0 < budget_s:
+        orc.sweep(tensors, weights, smat, model, 0.1, DIM)
+        sweeps += 1
+    return sweeps * N_E, time.perf_counter() - t0
+
+
+def cpu_baseline(cores, budget_s, min_sweeps=2):
+    """edge-updates/s of the oracle on `cores` host processes running concurrently (summed)."""
+    import multiprocessing as mp
+
+    if cores == 1:
+        res = [_cpu_worker((0, budget_s, min_sweeps))]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(s, budget_s, min_sweeps) for s in range(cores)])
+    return sum(n / t for n, t in res), sum(n for n, _ in res)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step_s = 4.0
+    for _ in range(args.warmup):
+        cpu_baseline(cores, 0.5, 1)
+    t0 = time.perf_counter()
+    edges = 0
+    for _ in range(args.steps):
+        _, n = cpu_baseline(cores, per_step_s, 2)
+        edges += n
+    dt = time.perf_counter() - t0
+    value = edges / dt
+    sample = f"{args.steps} steps x {cores} processes x >= {per_step_s:.0f} s of sweeps on one peps D=8 network each"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "host": "numpy/scipy oracle port of the reference algorithm, 1 BLAS thread per process"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+
+    import tnsu_b200 as tnsu
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    batch = args.batch
+    cplx = args.dtype == "c128"
+    sbytes = 16 if cplx else 8
+    stream = torch.cuda.Stream()
+    smat, tensors, weights = seeded_networks(batch, first_seed=rank * batch)
+    ham, gate = afh_operators()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    if cplx:
+        tensors = [t.astype(np.complex128) for t in tensors]
+    host_t = [pin(t) for t in tensors]
+    host_w = pin(weights)
+    out_w = [pin(np.empty((batch, DIM))) for _ in range(N_E)]
+
+    eng = tnsu.Engine(smat, D, [DIM] * N_E, DIM, cplx, batch=batch, device=local_rank, stream=stream.cuda_stream)
+    eng.reserve_gate_slots(1)
+    eng.set_gates(0, np.broadcast_to(gate, (batch, N_E, 4, 4)))
+    eng.set_hamiltonians(np.broadcast_to(ham, (batch, N_E, 4, 4)))
+
+    def upload():
+        for t in range(N_T):
+            eng.set_tensor(t, host_t[t])
+        for e in range(N_E):
+            eng.set_weights(e, host_w)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    upload()
+    # ---- resident-state timing: K sweeps, CUDA events on the engine stream ----
+    eng.sweep(0, args.warmup)
+    eng.synchronize()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            eng.sweep(0, args.steps)
+            ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    kern_ms, n_launch = eng.last_sweep_kernel_ms()
+    gpu_launches = eng.launch_count - launches0
+
+    # ---- end to end through the API with host buffers ----
+    def e2e_step():
+        upload()
+        eng.sweep(0, 1)
+        energies = eng.energy()
+        for e in range(N_E):
+            out_w[e][...] = eng.get_weights(e)
+        return energies
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        energies = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(t.nbytes for t in host_t) + N_E * host_w.nbytes
+    d2h = energies.nbytes + sum(w.nbytes for w in out_w)
+
+    # ---- max over ranks ----
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = (float(x) for x in times.cpu())
+    edges_per_step = world * batch * N_E
+    value = edges_per_step * args.steps / (ms * 1e-3)
+    e2e_value = edges_per_step * args.e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        alg_launch = algorithmic_bytes_per_edge(sbytes) * batch * N_E * args.steps / n_launch
+        achieved = alg_launch / (kern_ms * 1e-3 / n_launch) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_edge_kernel.json")))["dram_bytes_per_launch"]
+        except Exception:  # noqa: BLE001
+            pass
+        cores = 1
+        cpu_val, cpu_edges = cpu_baseline(cores, args.cpu_seconds)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128" if cplx else "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "edges_per_step": edges_per_step,
+                       "state_bytes_per_gpu": batch * N_T * D * DIM ** 4 * sbytes,
+                       "l2_policy": "inputs larger than L2 (state >> 126 MB), no flush",
+                       "arithmetic": "real float64 path (inputs with zero imaginary part)" if not cplx else "complex128 path",
+                       "parallelism": f"points sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps, "what": "upload state (pinned) + 1 sweep + energy_per_site + download energies and weights"},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
+                         "kernel": "edge_update_kernel", "launches": int(n_launch),
+                         "algorithmic_bytes_per_launch": alg_launch, "avg_launch_ms": kern_ms / n_launch,
+                         "note": "FP64-issue and latency co-limit this kernel at D=8 (DESIGN.md)"},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cpu_edges} edge updates of one peps D=8 network, numpy/scipy oracle, 1 BLAS thread"},
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="networks per GPU")
+    ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

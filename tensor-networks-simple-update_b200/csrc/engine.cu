@@ -1,0 +1,1221 @@
+// engine.cu — host side of libtnsu_b200.so: the C ABI of include/tnsu_b200.h, the edge scheduler
+// (dependency levels that preserve the reference's sequential edge order, SURVEY.md §7 "Order
+// dependence"), the bond-growth shape plan, kernel-variant selection and the batched run loop
+// (SimpleUpdate.run, reference src/tnsu/simple_update.py:107-194) with per-point state on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tnsu_b200.h"
+#include "edge_update.cuh"
+#include "rdm.cuh"
+
+static thread_local std::string g_create_error;
+
+#define SMEM_LIMIT (227 * 1024)
+
+struct LevelCfg {
+  int mm_t = 0;      // MMAX template (8/16/32)
+  int ncols = 1;     // NCOLS template
+  bool cluster = false;
+  int nt = 32;       // threads per side
+  int ldm = 0, lda = 0, ldv = 0;
+  EdgeSmem sm{};
+};
+
+struct tnsu_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n = 0, m = 0, d = 0, d_max = 0, dtype = 0, batch = 0, d4 = 0;
+  size_t ssz = 8;
+  std::vector<int64_t> smat;
+  struct Edge {
+    int t[2];
+    int leg[2];
+  };
+  std::vector<Edge> edges;
+  std::vector<std::vector<int>> t_edges;  // per tensor: edge id on each leg (leg = axis-1)
+  std::vector<int> level;
+  std::vector<std::vector<int>> level_edges;
+  std::vector<int> dims;                  // current bond dims
+  std::vector<long long> cap;             // per-tensor capacity (scalars) per point
+  int dcap = 1;
+  // device state
+  std::vector<void *> tens;
+  double *weights = nullptr, *tscale = nullptr, *edge_err = nullptr, *energy = nullptr;
+  void *gates = nullptr, *hams = nullptr, *op_buf = nullptr;
+  int n_slots = 0;
+  std::vector<char> slot_set;
+  bool hams_set = false;
+  cplx *pair_val = nullptr, *cval = nullptr, *rdm_buf = nullptr, *site_buf = nullptr;
+  EdgeDesc *d_descs = nullptr;
+  std::vector<EdgeDesc> h_descs;
+  std::vector<int> post_dims;
+  bool plan_valid = false, plan_steady = false;
+  std::vector<LevelCfg> cfgs;
+  int *d_level_edges = nullptr;
+  std::vector<int> level_off;
+  int *d_all_edges = nullptr;
+  SiteDesc *d_site = nullptr;
+  // run-loop state
+  int *r_slot = nullptr, *r_iter = nullptr, *r_step = nullptr, *r_active = nullptr, *r_conv = nullptr,
+      *r_nchecks = nullptr, *r_log_slot = nullptr, *r_log_step = nullptr, *r_nactive = nullptr, *r_islast = nullptr;
+  double *r_log_err = nullptr, *r_log_energy = nullptr;
+  int r_log_cap = 0;
+  int *h_nactive = nullptr;  // pinned
+  // debug buffers
+  void *dbg_li = nullptr, *dbg_lj = nullptr;
+  double *dbg_sigma = nullptr;
+  int *dbg_info = nullptr;
+  // bookkeeping
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_n = 0;
+  bool timed = false;
+};
+
+static int fail(tnsu_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e)
+    e->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _s = (call);                                                                         \
+    if (_s != cudaSuccess) return fail(e, TNSU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s)); \
+  } while (0)
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+static EdgeSmem make_edge_smem(size_t ssz, int mmax, int ldm, int lda, int ldv, int ncmax, int dcap, int d4,
+                               bool cluster) {
+  EdgeSmem s{};
+  int o = 0;
+  auto take = [&](int bytes) {
+    int at = o;
+    o = align16(o + bytes);
+    return at;
+  };
+  s.o_wleg = take(TNSU_MAX_LEGS * dcap * 8);
+  s.o_rowin = take(mmax * 8);
+  s.o_rowout = take(mmax * 8);
+  s.o_red = take(2 * TNSU_MAX_WARPS * mmax * (int)ssz);
+  s.o_colk = take(2 * mmax * (int)ssz);
+  s.o_mat_a = take(ldm * ldm * (int)ssz);
+  s.o_mat_b = take(ldm * ldm * (int)ssz);
+  s.o_mat_c = take(ldm * ldm * (int)ssz);
+  s.o_mat_d = take(ldm * ldm * (int)ssz);
+  s.o_tau = take(mmax * 8);
+  s.o_nred = take(TNSU_MAX_WARPS * 8);
+  s.side_bytes = o;
+  s.o_shared = cluster ? s.side_bytes : 2 * s.side_bytes;
+  o = 0;
+  s.o_svd_a = take(lda * ncmax * (int)ssz);
+  s.o_svd_v = take(ldv * ncmax * (int)ssz);
+  s.o_sig = take(TNSU_MAX_SVD * 8);
+  s.o_order = take(TNSU_MAX_SVD * 4);
+  s.o_lam_old = take(dcap * 8);
+  s.o_lam_new = take(dcap * 8);
+  s.o_flag = take(16);
+  s.o_gate = take(d4 * (int)ssz);
+  s.o_peer_l = take(cluster ? ldm * ldm * (int)ssz : 16);
+  s.o_peer_rt = take(cluster ? ldm * ldm * (int)ssz : 16);
+  s.total_bytes = s.o_shared + o;
+  return s;
+}
+
+static int max_threads(bool cplx_, int mm, int nc) {
+  int doubles = mm * nc * (cplx_ ? 2 : 1);
+  return doubles > 48 ? 256 : 512;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shape plan: simulate one sweep in the reference's edge order from the current bond dims
+// ---------------------------------------------------------------------------------------------
+static int plan_sweep(tnsu_engine *e) {
+  std::vector<int> cur = e->dims;
+  e->h_descs.assign(e->m, EdgeDesc{});
+  for (int ek = 0; ek < e->m; ++ek) {
+    EdgeDesc &ed = e->h_descs[ek];
+    ed.edge = ek;
+    ed.d = e->d;
+    ed.Dk = cur[ek];
+    for (int sd_i = 0; sd_i < 2; ++sd_i) {
+      SideDesc &sd = ed.s[sd_i];
+      int t = e->edges[ek].t[sd_i];
+      const std::vector<int> &legs = e->t_edges[t];
+      sd.tensor = t;
+      sd.base = e->tens[t];
+      sd.point_stride = e->cap[t];
+      sd.nlegs = (int)legs.size();
+      sd.bond_leg = e->edges[ek].leg[sd_i];
+      long long nprod = 1;
+      for (int l = 0; l < sd.nlegs; ++l) {
+        sd.dims[l] = cur[legs[l]];
+        sd.leg_edge[l] = legs[l];
+        if (l != sd.bond_leg) nprod *= sd.dims[l];
+      }
+      if (nprod > (1 << 20)) return fail(e, TNSU_E_UNSUPPORTED, "bond matrix of tensor %d has %lld columns", t, nprod);
+      sd.M = e->d * ed.Dk;
+      sd.N = (int)nprod;
+      sd.K = std::min(sd.M, sd.N);
+    }
+    ed.ni = ed.s[0].K * e->d;
+    ed.nj = e->d * ed.s[1].K;
+    ed.Dnew = std::min(e->d_max, std::min(ed.ni, ed.nj));
+    for (int sd_i = 0; sd_i < 2; ++sd_i) {
+      SideDesc &sd = ed.s[sd_i];
+      sd.Mout = e->d * ed.Dnew;
+      long long si = 1, so = 1;
+      for (int l = sd.nlegs - 1; l >= 0; --l) {
+        sd.in_stride[l] = si;
+        sd.out_stride[l] = so;
+        si *= sd.dims[l];
+        so *= (l == sd.bond_leg) ? ed.Dnew : sd.dims[l];
+      }
+      sd.in_stride_phys = si;
+      sd.out_stride_phys = so;
+      if (si * e->d > e->cap[sd.tensor] || so * e->d > e->cap[sd.tensor])
+        return fail(e, TNSU_E_STATE, "tensor %d outgrew its capacity", sd.tensor);
+    }
+    if (ed.Dnew > e->dcap) return fail(e, TNSU_E_STATE, "bond %d outgrew the weight capacity", ek);
+    cur[ek] = ed.Dnew;
+  }
+  e->post_dims = cur;
+  e->plan_steady = (cur == e->dims);
+
+  // per-level kernel configuration
+  e->cfgs.assign(e->level_edges.size(), LevelCfg{});
+  const bool cx = e->dtype == TNSU_C128;
+  for (size_t lv = 0; lv < e->level_edges.size(); ++lv) {
+    int maxM = 1, maxN = 1, maxnr = 1, maxnc = 1;
+    for (int ek : e->level_edges[lv]) {
+      const EdgeDesc &ed = e->h_descs[ek];
+      for (int s = 0; s < 2; ++s) {
+        maxM = std::max(maxM, std::max(ed.s[s].M, std::max(ed.s[s].Mout, ed.s[s].K)));
+        maxN = std::max(maxN, ed.s[s].N);
+      }
+      maxnr = std::max(maxnr, std::max(ed.ni, ed.nj));
+      maxnc = std::max(maxnc, std::min(ed.ni, ed.nj));
+    }
+    LevelCfg c;
+    c.mm_t = maxM <= 8 ? 8 : (maxM <= 16 ? 16 : 32);
+    if (maxM > TNSU_MAX_M)
+      return fail(e, TNSU_E_UNSUPPORTED, "bond matrix has %d rows (d*D); this build holds at most %d", maxM, TNSU_MAX_M);
+    if (maxnr > TNSU_MAX_SVD)
+      return fail(e, TNSU_E_UNSUPPORTED, "theta has %d rows; this build holds at most %d", maxnr, TNSU_MAX_SVD);
+    bool ok = false;
+    const bool modes[4] = {false, false, true, true};
+    const int ncs[4] = {1, 2, 1, 2};
+    for (int o = 0; o < 4 && !ok; ++o) {
+      int nt = ((maxN + ncs[o] - 1) / ncs[o] + 31) & ~31;
+      int lim = max_threads(cx, c.mm_t, ncs[o]);
+      if (!modes[o]) lim /= 2;
+      if (nt > lim || nt > TNSU_MAX_WARPS * 32) continue;
+      c.cluster = modes[o];
+      c.ncols = ncs[o];
+      c.nt = nt;
+      c.ldm = maxM | 1;
+      c.lda = maxnr | 1;
+      c.ldv = maxnc | 1;
+      c.sm = make_edge_smem(e->ssz, c.mm_t, c.ldm, c.lda, c.ldv, maxnc, e->dcap, e->d4, c.cluster);
+      if (c.sm.total_bytes > SMEM_LIMIT) continue;
+      ok = true;
+    }
+    if (!ok)
+      return fail(e, TNSU_E_UNSUPPORTED,
+                  "no kernel variant holds a %d x %d bond matrix (%s) on chip; reduce the bond dimension",
+                  maxM, maxN, cx ? "complex128" : "float64");
+    e->cfgs[lv] = c;
+  }
+  cudaError_t st = cudaMemcpyAsync(e->d_descs, e->h_descs.data(), sizeof(EdgeDesc) * e->m, cudaMemcpyHostToDevice,
+                                   e->stream);
+  if (st != cudaSuccess) return fail(e, TNSU_E_CUDA, "descriptor upload: %s", cudaGetErrorString(st));
+  // h_descs is pageable: the async copy is staged before returning, safe to reuse
+  e->plan_valid = true;
+  return TNSU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+// the kernel variants are instantiated in edge_inst.cu (one translation unit per scalar type and MMAX,
+// compiled in parallel); here they are only declared
+#define TNSU_EXTERN_VARIANT(S, MM, NC, CL) \
+  extern template cudaError_t launch_edge_variant<S, MM, NC, CL>(const EdgeLaunch<S> &, int, int, int, cudaStream_t);
+#define TNSU_EXTERN_MM(S, MM)            \
+  TNSU_EXTERN_VARIANT(S, MM, 1, false) \
+  TNSU_EXTERN_VARIANT(S, MM, 1, true)  \
+  TNSU_EXTERN_VARIANT(S, MM, 2, false) \
+  TNSU_EXTERN_VARIANT(S, MM, 2, true)
+TNSU_EXTERN_MM(double, 8)
+TNSU_EXTERN_MM(double, 16)
+TNSU_EXTERN_MM(double, 32)
+TNSU_EXTERN_MM(cplx, 8)
+TNSU_EXTERN_MM(cplx, 16)
+TNSU_EXTERN_VARIANT(cplx, 32, 1, false)
+TNSU_EXTERN_VARIANT(cplx, 32, 1, true)
+
+template <typename S>
+static cudaError_t launch_edge(const LevelCfg &c, const EdgeLaunch<S> &p, int n_work, cudaStream_t st) {
+  const int threads = c.cluster ? c.nt : 2 * c.nt;
+  const int smem = c.sm.total_bytes;
+#define VAR(MM, NC, CL) \
+  if (c.mm_t == MM && c.ncols == NC && c.cluster == CL) return launch_edge_variant<S, MM, NC, CL>(p, n_work, threads, smem, st);
+  VAR(8, 1, false)
+  VAR(8, 2, false)
+  VAR(8, 1, true)
+  VAR(8, 2, true)
+  VAR(16, 1, false)
+  VAR(16, 2, false)
+  VAR(16, 1, true)
+  VAR(16, 2, true)
+  VAR(32, 1, false)
+  VAR(32, 1, true)
+  if constexpr (sizeof(S) == 8) {
+    VAR(32, 2, false)
+    VAR(32, 2, true)
+  }
+#undef VAR
+  return cudaErrorInvalidConfiguration;
+}
+
+template <typename S>
+static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, const int *active, int only_edge,
+                      int dbg_point) {
+  for (size_t lv = 0; lv < e->level_edges.size(); ++lv) {
+    const LevelCfg &c = e->cfgs[lv];
+    EdgeLaunch<S> p{};
+    p.descs = e->d_descs;
+    p.level_edges = e->d_level_edges + e->level_off[lv];
+    p.n_level_edges = (int)e->level_edges[lv].size();
+    int batch = e->batch;
+    if (only_edge >= 0) {
+      if (e->level[only_edge] != (int)lv) continue;
+      p.level_edges = e->d_all_edges + only_edge;
+      p.n_level_edges = 1;
+    }
+    p.batch = batch;
+    p.m_edges = e->m;
+    p.dcap = e->dcap;
+    p.d4 = e->d4;
+    p.weights = e->weights;
+    p.tscale = e->tscale;
+    p.n_tensors = e->n;
+    p.gates = (const S *)e->gates;
+    p.gate_slot_stride = (long long)e->batch * e->m * e->d4;
+    p.point_slot = point_slot;
+    p.fixed_slot = fixed_slot;
+    p.active = active;
+    p.edge_err = e->edge_err;
+    p.nt_side = c.nt;
+    p.ldm = c.ldm;
+    p.lda = c.lda;
+    p.ldv = c.ldv;
+    p.sm = c.sm;
+    p.dbg_info = nullptr;
+    if (dbg_point >= 0) {
+      p.dbg_li = (S *)e->dbg_li;
+      p.dbg_lj = (S *)e->dbg_lj;
+      p.dbg_sigma = e->dbg_sigma;
+      p.dbg_info = e->dbg_info;
+      p.dbg_point = dbg_point;
+    }
+    cudaError_t st = launch_edge<S>(c, p, batch * p.n_level_edges, e->stream);
+    if (st != cudaSuccess)
+      return fail(e, TNSU_E_CUDA, "edge kernel launch (level %zu, MM=%d NC=%d cluster=%d nt=%d smem=%d): %s", lv,
+                  c.mm_t, c.ncols, (int)c.cluster, c.nt, c.sm.total_bytes, cudaGetErrorString(st));
+    e->launches++;
+    e->last_n++;
+  }
+  return TNSU_OK;
+}
+
+static int one_sweep(tnsu_engine *e, int fixed_slot, const int *point_slot, const int *active) {
+  if (!e->plan_valid) {
+    int rc = plan_sweep(e);
+    if (rc) return rc;
+  }
+  int rc = (e->dtype == TNSU_C128) ? run_levels<cplx>(e, fixed_slot, point_slot, active, -1, -1)
+                                   : run_levels<double>(e, fixed_slot, point_slot, active, -1, -1);
+  if (rc) return rc;
+  if (!e->plan_steady) {
+    e->dims = e->post_dims;
+    e->plan_valid = false;
+  }
+  return TNSU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RDM launches
+// ---------------------------------------------------------------------------------------------
+static int pair_smem_bytes(const tnsu_engine *e, int M) {
+  return (int)(2 * M * M * e->ssz + M * (RDM_CHUNK + 1) * e->ssz + RDM_CHUNK * 8 + RDM_CHUNK * 8 +
+               TNSU_MAX_LEGS * e->dcap * 8 + e->dcap * 8 + e->d4 * 16 + 64 * 16);
+}
+
+template <typename S>
+static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S *ops, long long op_pstride,
+                       long long op_estride, cplx *pair_val, cplx *rdm_out, const int *iter_state, const int *active) {
+  // the caller (ensure_static_descs) has put descriptors of the CURRENT shapes on the device
+  int maxM = 1;
+  for (int ek = 0; ek < e->m; ++ek) maxM = std::max(maxM, e->d * e->dims[ek]);
+  PairRdmLaunch<S> p{};
+  p.descs = e->d_descs;
+  p.edge_list = edge_list;
+  p.n_list = n_list;
+  p.batch = e->batch;
+  p.m_edges = e->m;
+  p.dcap = e->dcap;
+  p.d4 = e->d4;
+  p.weights = e->weights;
+  p.ops = ops;
+  p.op_point_stride = op_pstride;
+  p.op_edge_stride = op_estride;
+  p.pair_val = pair_val;
+  p.rdm_out = rdm_out;
+  p.iter_state = iter_state;
+  p.active = active;
+  int smem = pair_smem_bytes(e, maxM);
+  if (smem > SMEM_LIMIT) return fail(e, TNSU_E_UNSUPPORTED, "pair RDM needs %d bytes of shared memory", smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(pair_rdm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_done = true;
+  }
+  pair_rdm_kernel<S><<<e->batch * n_list, RDM_THREADS, smem, e->stream>>>(p);
+  CK(cudaGetLastError());
+  e->launches++;
+  return TNSU_OK;
+}
+
+// RDMs need descriptors of the CURRENT shapes for every edge (not the mid-sweep ones).  In steady state
+// the sweep plan is exactly that; otherwise build a static plan with Dnew = Dk semantics.
+static int ensure_static_descs(tnsu_engine *e) {
+  if (!e->plan_valid) {
+    int rc = plan_sweep(e);
+    if (rc) return rc;
+  }
+  if (e->plan_steady) return TNSU_OK;
+  // not steady: overwrite the device descriptors with "current shape" descriptors (input side only is read)
+  std::vector<EdgeDesc> st = e->h_descs;
+  for (int ek = 0; ek < e->m; ++ek) {
+    EdgeDesc &ed = st[ek];
+    ed.Dk = e->dims[ek];
+    for (int s = 0; s < 2; ++s) {
+      SideDesc &sd = ed.s[s];
+      const std::vector<int> &legs = e->t_edges[sd.tensor];
+      long long nprod = 1, si = 1;
+      for (int l = 0; l < sd.nlegs; ++l) sd.dims[l] = e->dims[legs[l]];
+      for (int l = sd.nlegs - 1; l >= 0; --l) {
+        sd.in_stride[l] = si;
+        si *= sd.dims[l];
+        if (l != sd.bond_leg) nprod *= sd.dims[l];
+      }
+      sd.in_stride_phys = si;
+      sd.M = e->d * ed.Dk;
+      sd.N = (int)nprod;
+    }
+  }
+  CK(cudaMemcpyAsync(e->d_descs, st.data(), sizeof(EdgeDesc) * e->m, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->plan_valid = false;  // the sweep plan on the device was overwritten; rebuild before the next sweep
+  return TNSU_OK;
+}
+
+static int upload_site_descs(tnsu_engine *e) {
+  std::vector<SiteDesc> sd(e->n);
+  for (int t = 0; t < e->n; ++t) {
+    sd[t].base = e->tens[t];
+    sd[t].point_stride = e->cap[t];
+    sd[t].nlegs = (int)e->t_edges[t].size();
+    long long nv = 1;
+    for (int l = 0; l < sd[t].nlegs; ++l) {
+      sd[t].dims[l] = e->dims[e->t_edges[t][l]];
+      sd[t].leg_edge[l] = e->t_edges[t][l];
+      nv *= sd[t].dims[l];
+    }
+    sd[t].nvirt = nv;
+  }
+  CK(cudaMemcpyAsync(e->d_site, sd.data(), sizeof(SiteDesc) * e->n, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// run-loop state machine (simple_update.py:117-194), one thread per point
+// ---------------------------------------------------------------------------------------------
+struct RunState {
+  int batch, m_edges, n_dts, max_iter, log_cap;
+  double tol;
+  int *slot, *iter, *step, *active, *conv, *nchecks, *log_slot, *log_step, *nactive;
+  const int *is_last;
+  double *log_err, *log_energy;
+  const double *edge_err, *energy;
+};
+
+__global__ void run_state_kernel(RunState s) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.batch || s.active[b] == 0) return;
+  int i = s.iter[b];
+  int slot = s.slot[b];
+  s.step[b] += 1;
+  bool advance = false;
+  if (i % 2 == 0 && i > 0) {
+    double err = 0.0;
+    bool bad = false;
+    for (int e = 0; e < s.m_edges; ++e) {
+      double v = s.edge_err[(size_t)b * s.m_edges + e];
+      if (v != v) bad = true;
+      err = fmax(err, v);
+    }
+    if (bad) err = nan("");
+    const int k = s.nchecks[b];
+    if (k < s.log_cap) {
+      s.log_err[(size_t)b * s.log_cap + k] = err;
+      s.log_energy[(size_t)b * s.log_cap + k] = s.energy[b];
+      s.log_slot[(size_t)b * s.log_cap + k] = slot;
+      s.log_step[(size_t)b * s.log_cap + k] = s.step[b];
+    }
+    s.nchecks[b] = k + 1;
+    if (err <= s.tol && s.is_last[slot]) {
+      s.conv[b] = 1;
+      s.active[b] = 0;
+      return;
+    }
+    if (err <= s.tol) advance = true;
+  }
+  if (!advance) {
+    i += 1;
+    if (i >= s.max_iter)
+      advance = true;
+    else
+      s.iter[b] = i;
+  }
+  if (advance) {
+    slot += 1;
+    s.iter[b] = 0;
+    if (slot >= s.n_dts) {
+      s.active[b] = 0;
+      return;
+    }
+    s.slot[b] = slot;
+  }
+  atomicAdd(s.nactive, 1);
+}
+
+__global__ void fill_int_kernel(int *p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void fill_double_kernel(double *p, long long n, double v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int tnsu_abi_version(void) { return TNSU_ABI_VERSION; }
+
+const char *tnsu_last_error(const tnsu_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int tnsu_schedule_levels(int n, int m, const int64_t *smat, int32_t *level_out) {
+  if (!smat || !level_out || n <= 0 || m <= 0) return fail(nullptr, TNSU_E_ARG, "schedule_levels: bad argument");
+  std::vector<int> last(n, -1);
+  int nl = 0;
+  for (int ek = 0; ek < m; ++ek) {
+    int ends[2], cnt = 0;
+    for (int t = 0; t < n; ++t)
+      if (smat[(size_t)t * m + ek] > 0) {
+        if (cnt < 2) ends[cnt] = t;
+        ++cnt;
+      }
+    if (cnt != 2) return fail(nullptr, TNSU_E_ARG, "edge %d is not connected to exactly two tensors", ek);
+    int lv = std::max(last[ends[0]], last[ends[1]]) + 1;
+    level_out[ek] = lv;
+    last[ends[0]] = last[ends[1]] = lv;
+    nl = std::max(nl, lv + 1);
+  }
+  return nl;
+}
+
+int tnsu_destroy(tnsu_engine *e) {
+  if (!e) return TNSU_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void *p : e->tens) cudaFree(p);
+  void *ptrs[] = {e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
+                  e->rdm_buf, e->site_buf, e->d_descs, e->d_level_edges, e->d_all_edges, e->d_site, e->r_slot,
+                  e->r_iter, e->r_step, e->r_active, e->r_conv, e->r_nchecks, e->r_log_slot, e->r_log_step,
+                  e->r_nactive, e->r_islast, e->r_log_err, e->r_log_energy, e->dbg_li, e->dbg_lj, e->dbg_sigma,
+                  e->dbg_info};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (e->h_nactive) cudaFreeHost(e->h_nactive);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return TNSU_OK;
+}
+
+int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, const int32_t *edge_dims, int d_max,
+                int dtype, int batch, int device, void *stream) {
+  tnsu_engine *e = nullptr;
+  if (!out || !smat || !edge_dims) return fail(e, TNSU_E_ARG, "null argument");
+  *out = nullptr;
+  if (n <= 0 || m <= 0 || batch <= 0) return fail(e, TNSU_E_ARG, "n, m and batch must be positive");
+  if (d < 1 || d > TNSU_MAX_SPIN) return fail(e, TNSU_E_UNSUPPORTED, "physical dimension %d not in 1..%d", d, TNSU_MAX_SPIN);
+  if (dtype != TNSU_F64 && dtype != TNSU_C128) return fail(e, TNSU_E_ARG, "dtype must be TNSU_F64 or TNSU_C128");
+  if (d_max < 1) return fail(e, TNSU_E_ARG, "d_max must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(e, TNSU_E_CUDA, "no CUDA device: the Simple-Update engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(e, TNSU_E_ARG, "device %d out of range (%d devices)", device, ndev);
+
+  // structure-matrix validation (structure_matrix_constructor.py:148-178)
+  std::vector<std::vector<int>> t_edges(n);
+  for (int t = 0; t < n; ++t) {
+    std::vector<std::pair<int, int>> ax;  // (axis, edge)
+    for (int ek = 0; ek < m; ++ek) {
+      int64_t a = smat[(size_t)t * m + ek];
+      if (a < 0) return fail(e, TNSU_E_ARG, "negative structure-matrix entry");
+      if (a > 0) ax.push_back({(int)a, ek});
+    }
+    std::sort(ax.begin(), ax.end());
+    if ((int)ax.size() > TNSU_MAX_LEGS)
+      return fail(e, TNSU_E_UNSUPPORTED, "tensor %d has %zu legs; this build holds at most %d", t, ax.size(), TNSU_MAX_LEGS);
+    if (ax.empty()) return fail(e, TNSU_E_ARG, "tensor %d has no legs", t);
+    for (size_t l = 0; l < ax.size(); ++l) {
+      if (ax[l].first != (int)l + 1) return fail(e, TNSU_E_ARG, "row %d of the structure matrix is not a permutation of 1..z", t);
+      t_edges[t].push_back(ax[l].second);
+    }
+  }
+  std::vector<tnsu_engine::Edge> edges(m);
+  for (int ek = 0; ek < m; ++ek) {
+    int cnt = 0;
+    for (int t = 0; t < n; ++t) {
+      int64_t a = smat[(size_t)t * m + ek];
+      if (a > 0) {
+        if (cnt < 2) {
+          edges[ek].t[cnt] = t;
+          edges[ek].leg[cnt] = (int)a - 1;
+        }
+        ++cnt;
+      }
+    }
+    if (cnt != 2) return fail(e, TNSU_E_ARG, "edge %d is not connected to exactly two tensors", ek);
+    if (edge_dims[ek] < 1) return fail(e, TNSU_E_ARG, "edge %d has dimension %d", ek, edge_dims[ek]);
+  }
+
+  e = new tnsu_engine();
+  e->device = device;
+  e->n = n;
+  e->m = m;
+  e->d = d;
+  e->d4 = d * d * d * d;
+  e->d_max = d_max;
+  e->dtype = dtype;
+  e->ssz = dtype == TNSU_C128 ? 16 : 8;
+  e->batch = batch;
+  e->smat.assign(smat, smat + (size_t)n * m);
+  e->edges = edges;
+  e->t_edges = t_edges;
+  e->dims.assign(edge_dims, edge_dims + m);
+
+  // dependency levels: an edge waits for every EARLIER edge that shares a tensor with it
+  e->level.assign(m, 0);
+  {
+    std::vector<int> last_level_of_tensor(n, -1);
+    int nl = 0;
+    for (int ek = 0; ek < m; ++ek) {
+      int lv = std::max(last_level_of_tensor[edges[ek].t[0]], last_level_of_tensor[edges[ek].t[1]]) + 1;
+      e->level[ek] = lv;
+      last_level_of_tensor[edges[ek].t[0]] = lv;
+      last_level_of_tensor[edges[ek].t[1]] = lv;
+      nl = std::max(nl, lv + 1);
+    }
+    e->level_edges.assign(nl, {});
+    for (int ek = 0; ek < m; ++ek) e->level_edges[e->level[ek]].push_back(ek);
+  }
+
+  // shape trajectory -> capacities
+  {
+    std::vector<int> cur = e->dims;
+    e->cap.assign(n, 0);
+    int dcap = 1;
+    auto account = [&]() {
+      for (int t = 0; t < n; ++t) {
+        long long el = d;
+        for (int ek : t_edges[t]) el *= cur[ek];
+        e->cap[t] = std::max(e->cap[t], el);
+      }
+      for (int ek = 0; ek < m; ++ek) dcap = std::max(dcap, cur[ek]);
+    };
+    account();
+    for (int sweep = 0; sweep < 64; ++sweep) {
+      bool changed = false;
+      for (int ek = 0; ek < m; ++ek) {
+        long long k[2];
+        for (int s = 0; s < 2; ++s) {
+          long long nprod = 1;
+          for (int el : t_edges[edges[ek].t[s]])
+            if (el != ek) nprod = std::min<long long>(nprod * cur[el], 1LL << 40);
+          k[s] = std::min<long long>((long long)d * cur[ek], nprod);
+        }
+        long long dn = std::min<long long>(d_max, std::min(k[0] * d, k[1] * d));
+        if (dn != cur[ek]) changed = true;
+        cur[ek] = (int)dn;
+        account();
+        if (dcap > 64) {
+          delete e;
+          return fail(nullptr, TNSU_E_UNSUPPORTED, "bond dimension grows past 64");
+        }
+      }
+      if (!changed) break;
+    }
+    e->dcap = dcap;
+    for (int t = 0; t < n; ++t) e->cap[t] = (e->cap[t] + 1) & ~1LL;  // keep 16-byte alignment per point
+  }
+
+#define CKC(call)                                                                                \
+  do {                                                                                           \
+    cudaError_t _s = (call);                                                                     \
+    if (_s != cudaSuccess) {                                                                     \
+      fail(nullptr, TNSU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s));                \
+      tnsu_destroy(e);                                                                           \
+      return TNSU_E_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+  CKC(cudaSetDevice(device));
+  if (stream) {
+    e->stream = (cudaStream_t)stream;
+  } else {
+    CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+  }
+  e->tens.assign(n, nullptr);
+  for (int t = 0; t < n; ++t) {
+    CKC(cudaMalloc(&e->tens[t], (size_t)batch * e->cap[t] * e->ssz));
+    CKC(cudaMemsetAsync(e->tens[t], 0, (size_t)batch * e->cap[t] * e->ssz, e->stream));
+  }
+  size_t B = batch;
+  CKC(cudaMalloc(&e->weights, B * m * e->dcap * 8));
+  CKC(cudaMemsetAsync(e->weights, 0, B * m * e->dcap * 8, e->stream));
+  CKC(cudaMalloc(&e->tscale, B * n * 8));
+  CKC(cudaMalloc(&e->edge_err, B * m * 8));
+  CKC(cudaMemsetAsync(e->edge_err, 0, B * m * 8, e->stream));
+  CKC(cudaMalloc(&e->energy, B * 8));
+  CKC(cudaMalloc(&e->pair_val, B * m * 16));
+  CKC(cudaMalloc(&e->cval, B * 16));
+  CKC(cudaMalloc(&e->rdm_buf, B * e->d4 * 16));
+  CKC(cudaMalloc(&e->site_buf, B * n * d * d * 16));
+  CKC(cudaMalloc(&e->hams, B * m * e->d4 * e->ssz));
+  CKC(cudaMalloc(&e->op_buf, (size_t)e->d4 * e->ssz));
+  CKC(cudaMalloc(&e->d_descs, sizeof(EdgeDesc) * m));
+  CKC(cudaMalloc(&e->d_site, sizeof(SiteDesc) * n));
+  {
+    std::vector<int> flat;
+    for (auto &lv : e->level_edges) {
+      e->level_off.push_back((int)flat.size());
+      flat.insert(flat.end(), lv.begin(), lv.end());
+    }
+    CKC(cudaMalloc(&e->d_level_edges, sizeof(int) * m));
+    CKC(cudaMemcpy(e->d_level_edges, flat.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+    std::vector<int> all(m);
+    for (int i = 0; i < m; ++i) all[i] = i;
+    CKC(cudaMalloc(&e->d_all_edges, sizeof(int) * m));
+    CKC(cudaMemcpy(e->d_all_edges, all.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  }
+  CKC(cudaMalloc(&e->r_slot, B * 4));
+  CKC(cudaMalloc(&e->r_iter, B * 4));
+  CKC(cudaMalloc(&e->r_step, B * 4));
+  CKC(cudaMalloc(&e->r_active, B * 4));
+  CKC(cudaMalloc(&e->r_conv, B * 4));
+  CKC(cudaMalloc(&e->r_nchecks, B * 4));
+  CKC(cudaMalloc(&e->r_nactive, 4));
+  CKC(cudaMallocHost(&e->h_nactive, 4));
+  CKC(cudaMalloc(&e->dbg_li, 64 * 64 * 16));
+  CKC(cudaMalloc(&e->dbg_lj, 64 * 64 * 16));
+  CKC(cudaMalloc(&e->dbg_sigma, 64 * 8));
+  CKC(cudaMalloc(&e->dbg_info, 16 * 4));
+  CKC(cudaEventCreate(&e->ev0));
+  CKC(cudaEventCreate(&e->ev1));
+  fill_double_kernel<<<(int)((B * n + 255) / 256), 256, 0, e->stream>>>(e->tscale, (long long)(B * n), 1.0);
+  CKC(cudaGetLastError());
+  CKC(cudaStreamSynchronize(e->stream));
+#undef CKC
+  {
+    // validate eagerly: the first sweep's shapes must fit a kernel variant (later growth is checked as it happens)
+    int rc = plan_sweep(e);
+    if (rc) {
+      g_create_error = e->err;
+      tnsu_destroy(e);
+      return rc;
+    }
+  }
+  *out = e;
+  return TNSU_OK;
+}
+
+int tnsu_edge_dims(const tnsu_engine *e, int32_t *dims_out) {
+  if (!e || !dims_out) return TNSU_E_ARG;
+  for (int i = 0; i < e->m; ++i) dims_out[i] = e->dims[i];
+  return TNSU_OK;
+}
+
+int64_t tnsu_tensor_elems(const tnsu_engine *e, int t) {
+  if (!e || t < 0 || t >= e->n) return -1;
+  long long el = e->d;
+  for (int ek : e->t_edges[t]) el *= e->dims[ek];
+  return el;
+}
+
+int tnsu_num_levels(const tnsu_engine *e) { return e ? (int)e->level_edges.size() : TNSU_E_ARG; }
+
+int tnsu_edge_levels(const tnsu_engine *e, int32_t *level_out) {
+  if (!e || !level_out) return TNSU_E_ARG;
+  for (int i = 0; i < e->m; ++i) level_out[i] = e->level[i];
+  return TNSU_OK;
+}
+
+int tnsu_set_tensor(tnsu_engine *e, int t, const void *host, int64_t elems) {
+  if (!e) return TNSU_E_ARG;
+  if (!host || t < 0 || t >= e->n) return fail(e, TNSU_E_ARG, "set_tensor: bad argument");
+  if (elems != tnsu_tensor_elems(e, t))
+    return fail(e, TNSU_E_ARG, "set_tensor: tensor %d has %lld elements per point, got %lld", t,
+                (long long)tnsu_tensor_elems(e, t), (long long)elems);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy2DAsync(e->tens[t], e->cap[t] * e->ssz, host, elems * e->ssz, elems * e->ssz, e->batch,
+                       cudaMemcpyHostToDevice, e->stream));
+  reset_scale_kernel<<<(e->batch + 255) / 256, 256, 0, e->stream>>>(e->tscale, e->n, e->batch, t);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int tnsu_get_tensor(tnsu_engine *e, int t, void *host, int64_t elems) {
+  if (!e) return TNSU_E_ARG;
+  if (!host || t < 0 || t >= e->n) return fail(e, TNSU_E_ARG, "get_tensor: bad argument");
+  if (elems != tnsu_tensor_elems(e, t))
+    return fail(e, TNSU_E_ARG, "get_tensor: tensor %d has %lld elements per point, got %lld", t,
+                (long long)tnsu_tensor_elems(e, t), (long long)elems);
+  CK(cudaSetDevice(e->device));
+  dim3 grid((unsigned)std::min<long long>((elems + 255) / 256, 1024), e->batch);
+  if (e->dtype == TNSU_C128)
+    apply_scale_kernel<cplx><<<grid, 256, 0, e->stream>>>((cplx *)e->tens[t], e->cap[t], elems, e->batch, e->tscale, e->n, t);
+  else
+    apply_scale_kernel<double><<<grid, 256, 0, e->stream>>>((double *)e->tens[t], e->cap[t], elems, e->batch, e->tscale, e->n, t);
+  CK(cudaGetLastError());
+  reset_scale_kernel<<<(e->batch + 255) / 256, 256, 0, e->stream>>>(e->tscale, e->n, e->batch, t);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(host, elems * e->ssz, e->tens[t], e->cap[t] * e->ssz, elems * e->ssz, e->batch,
+                       cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int tnsu_set_weights(tnsu_engine *e, int edge, const double *host, int len) {
+  if (!e) return TNSU_E_ARG;
+  if (!host || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "set_weights: bad argument");
+  if (len != e->dims[edge]) return fail(e, TNSU_E_ARG, "set_weights: edge %d has dimension %d, got %d", edge, e->dims[edge], len);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy2DAsync(e->weights + (size_t)edge * e->dcap, (size_t)e->m * e->dcap * 8, host, (size_t)len * 8,
+                       (size_t)len * 8, e->batch, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int tnsu_get_weights(tnsu_engine *e, int edge, double *host, int len) {
+  if (!e) return TNSU_E_ARG;
+  if (!host || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "get_weights: bad argument");
+  if (len != e->dims[edge]) return fail(e, TNSU_E_ARG, "get_weights: edge %d has dimension %d, got %d", edge, e->dims[edge], len);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy2DAsync(host, (size_t)len * 8, e->weights + (size_t)edge * e->dcap, (size_t)e->m * e->dcap * 8,
+                       (size_t)len * 8, e->batch, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+static int upload_c128(tnsu_engine *e, void *dst, const void *src_c128, size_t count) {
+  CK(cudaSetDevice(e->device));
+  if (e->dtype == TNSU_C128) {
+    CK(cudaMemcpyAsync(dst, src_c128, count * 16, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  } else {
+    const double *s = (const double *)src_c128;
+    std::vector<double> re_(count);
+    for (size_t i = 0; i < count; ++i) re_[i] = s[2 * i];
+    CK(cudaMemcpyAsync(dst, re_.data(), count * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return TNSU_OK;
+}
+
+int tnsu_reserve_gate_slots(tnsu_engine *e, int n_slots) {
+  if (!e) return TNSU_E_ARG;
+  if (n_slots < 1) return fail(e, TNSU_E_ARG, "n_slots must be >= 1");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->gates) CK(cudaFree(e->gates));
+  e->gates = nullptr;
+  CK(cudaMalloc(&e->gates, (size_t)n_slots * e->batch * e->m * e->d4 * e->ssz));
+  e->n_slots = n_slots;
+  e->slot_set.assign(n_slots, 0);
+  return TNSU_OK;
+}
+
+int tnsu_set_gates(tnsu_engine *e, int slot, const void *gates) {
+  if (!e) return TNSU_E_ARG;
+  if (!gates || slot < 0 || slot >= e->n_slots) return fail(e, TNSU_E_ARG, "set_gates: slot %d of %d", slot, e->n_slots);
+  size_t count = (size_t)e->batch * e->m * e->d4;
+  int rc = upload_c128(e, (char *)e->gates + (size_t)slot * count * e->ssz, gates, count);
+  if (rc) return rc;
+  e->slot_set[slot] = 1;
+  return TNSU_OK;
+}
+
+int tnsu_set_hamiltonians(tnsu_engine *e, const void *ham) {
+  if (!e) return TNSU_E_ARG;
+  if (!ham) return fail(e, TNSU_E_ARG, "set_hamiltonians: null");
+  int rc = upload_c128(e, e->hams, ham, (size_t)e->batch * e->m * e->d4);
+  if (rc) return rc;
+  e->hams_set = true;
+  return TNSU_OK;
+}
+
+int tnsu_sweep(tnsu_engine *e, int slot, int n_sweeps) {
+  if (!e) return TNSU_E_ARG;
+  if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "sweep: gates of slot %d not set", slot);
+  CK(cudaSetDevice(e->device));
+  e->last_n = 0;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (int s = 0; s < n_sweeps; ++s) {
+    int rc = one_sweep(e, slot, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->timed = true;
+  return TNSU_OK;
+}
+
+int tnsu_last_sweep_kernel_ms(tnsu_engine *e, double *total_ms, int32_t *n_launches) {
+  if (!e) return TNSU_E_ARG;
+  if (!e->timed) return fail(e, TNSU_E_STATE, "no sweep has been timed");
+  CK(cudaEventSynchronize(e->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  if (total_ms) *total_ms = ms;
+  if (n_launches) *n_launches = e->last_n;
+  return TNSU_OK;
+}
+
+int tnsu_sweep_error(tnsu_engine *e, double *err_out) {
+  if (!e) return TNSU_E_ARG;
+  if (!err_out) return fail(e, TNSU_E_ARG, "sweep_error: null");
+  CK(cudaSetDevice(e->device));
+  std::vector<double> h((size_t)e->batch * e->m);
+  CK(cudaMemcpyAsync(h.data(), e->edge_err, h.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int b = 0; b < e->batch; ++b) {
+    double mx = 0.0;
+    bool bad = false;
+    for (int ek = 0; ek < e->m; ++ek) {
+      double v = h[(size_t)b * e->m + ek];
+      if (v != v) bad = true;
+      mx = std::max(mx, v);
+    }
+    err_out[b] = bad ? NAN : mx;
+  }
+  return TNSU_OK;
+}
+
+static int energy_launch(tnsu_engine *e, const int *iter_state, const int *active) {
+  int rc;
+  if (e->dtype == TNSU_C128)
+    rc = launch_pair<cplx>(e, e->d_all_edges, e->m, (const cplx *)e->hams, (long long)e->m * e->d4, e->d4, e->pair_val,
+                           nullptr, iter_state, active);
+  else
+    rc = launch_pair<double>(e, e->d_all_edges, e->m, (const double *)e->hams, (long long)e->m * e->d4, e->d4,
+                             e->pair_val, nullptr, iter_state, active);
+  if (rc) return rc;
+  pair_sum_kernel<<<(e->batch + 127) / 128, 128, 0, e->stream>>>(e->pair_val, e->batch, e->m, e->n, e->energy, e->cval,
+                                                                 iter_state, active);
+  CK(cudaGetLastError());
+  e->launches++;
+  return TNSU_OK;
+}
+
+int tnsu_energy(tnsu_engine *e, double *energy_out) {
+  if (!e) return TNSU_E_ARG;
+  if (!energy_out) return fail(e, TNSU_E_ARG, "energy: null");
+  if (!e->hams_set) return fail(e, TNSU_E_STATE, "energy: Hamiltonians not set");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_static_descs(e);
+  if (rc) return rc;
+  rc = energy_launch(e, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(energy_out, e->energy, (size_t)e->batch * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;  // NaN/Inf energies are returned as they are, like the reference does
+}
+
+int tnsu_pair_rdm(tnsu_engine *e, int edge, void *rdm) {
+  if (!e) return TNSU_E_ARG;
+  if (!rdm || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "pair_rdm: bad argument");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_static_descs(e);
+  if (rc) return rc;
+  if (e->dtype == TNSU_C128)
+    rc = launch_pair<cplx>(e, e->d_all_edges + edge, 1, nullptr, 0, 0, nullptr, e->rdm_buf, nullptr, nullptr);
+  else
+    rc = launch_pair<double>(e, e->d_all_edges + edge, 1, nullptr, 0, 0, nullptr, e->rdm_buf, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(rdm, e->rdm_buf, (size_t)e->batch * e->d4 * 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+static int site_rdms(tnsu_engine *e, std::vector<cplx> &h) {
+  CK(cudaSetDevice(e->device));
+  int rc = upload_site_descs(e);
+  if (rc) return rc;
+  if (e->dcap > 64) return fail(e, TNSU_E_UNSUPPORTED, "site RDM: bond dimension above 64");
+  if (e->dtype == TNSU_C128)
+    site_rdm_kernel<cplx><<<e->batch * e->n, RDM_THREADS, 0, e->stream>>>(e->d_site, e->n, e->d, e->batch, e->m, e->dcap,
+                                                                           e->weights, e->site_buf);
+  else
+    site_rdm_kernel<double><<<e->batch * e->n, RDM_THREADS, 0, e->stream>>>(e->d_site, e->n, e->d, e->batch, e->m, e->dcap,
+                                                                             e->weights, e->site_buf);
+  CK(cudaGetLastError());
+  e->launches++;
+  h.resize((size_t)e->batch * e->n * e->d * e->d);
+  CK(cudaMemcpyAsync(h.data(), e->site_buf, h.size() * 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int tnsu_site_rdm(tnsu_engine *e, int t, void *rdm) {
+  if (!e) return TNSU_E_ARG;
+  if (!rdm || t < 0 || t >= e->n) return fail(e, TNSU_E_ARG, "site_rdm: bad argument");
+  std::vector<cplx> h;
+  int rc = site_rdms(e, h);
+  if (rc) return rc;
+  const int dd = e->d * e->d;
+  cplx *out = (cplx *)rdm;
+  for (int b = 0; b < e->batch; ++b)
+    for (int i = 0; i < dd; ++i) out[(size_t)b * dd + i] = h[((size_t)b * e->n + t) * dd + i];
+  return TNSU_OK;
+}
+
+int tnsu_expectation_per_site(tnsu_engine *e, const void *op, void *out) {
+  if (!e) return TNSU_E_ARG;
+  if (!op || !out) return fail(e, TNSU_E_ARG, "expectation_per_site: null");
+  std::vector<cplx> h;
+  int rc = site_rdms(e, h);
+  if (rc) return rc;
+  const int d = e->d, dd = d * d;
+  const cplx *o = (const cplx *)op;
+  cplx *res = (cplx *)out;
+  for (int b = 0; b < e->batch; ++b) {
+    cplx tot = mkc(0, 0);
+    for (int t = 0; t < e->n; ++t) {
+      const cplx *r = &h[((size_t)b * e->n + t) * dd];
+      for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) tot += r[i * d + j] * o[j * d + i];  // trace(rho @ O)
+    }
+    res[b] = tot * (1.0 / e->n);
+  }
+  return TNSU_OK;
+}
+
+int tnsu_pair_expectation_per_site(tnsu_engine *e, const void *op, void *out) {
+  if (!e) return TNSU_E_ARG;
+  if (!op || !out) return fail(e, TNSU_E_ARG, "pair_expectation_per_site: null");
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_static_descs(e);
+  if (rc) return rc;
+  rc = upload_c128(e, e->op_buf, op, (size_t)e->d4);
+  if (rc) return rc;
+  if (e->dtype == TNSU_C128)
+    rc = launch_pair<cplx>(e, e->d_all_edges, e->m, (const cplx *)e->op_buf, 0, 0, e->pair_val, nullptr, nullptr, nullptr);
+  else
+    rc = launch_pair<double>(e, e->d_all_edges, e->m, (const double *)e->op_buf, 0, 0, e->pair_val, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  pair_sum_kernel<<<(e->batch + 127) / 128, 128, 0, e->stream>>>(e->pair_val, e->batch, e->m, e->n, nullptr, e->cval,
+                                                                 nullptr, nullptr);
+  CK(cudaGetLastError());
+  e->launches++;
+  CK(cudaMemcpyAsync(out, e->cval, (size_t)e->batch * 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_iterations, double tol, int log_cap,
+             int32_t *n_checks, double *log_error, double *log_energy, int32_t *log_slot, int32_t *log_step,
+             int32_t *converged, int32_t *total_sweeps) {
+  if (!e) return TNSU_E_ARG;
+  if (n_dts < 0 || n_dts > e->n_slots) return fail(e, TNSU_E_ARG, "run: %d time steps but %d gate slots", n_dts, e->n_slots);
+  for (int s = 0; s < n_dts; ++s)
+    if (!e->slot_set[s]) return fail(e, TNSU_E_STATE, "run: gates of slot %d not set", s);
+  if (!e->hams_set) return fail(e, TNSU_E_STATE, "run: Hamiltonians not set");
+  if (!is_last_value && n_dts > 0) return fail(e, TNSU_E_ARG, "run: null is_last_value");
+  if (log_cap < 0) return fail(e, TNSU_E_ARG, "run: negative log_cap");
+  CK(cudaSetDevice(e->device));
+  const size_t B = e->batch;
+  // (re)allocate logs
+  if (log_cap > e->r_log_cap || !e->r_log_err) {
+    if (e->r_log_err) cudaFree(e->r_log_err);
+    if (e->r_log_energy) cudaFree(e->r_log_energy);
+    if (e->r_log_slot) cudaFree(e->r_log_slot);
+    if (e->r_log_step) cudaFree(e->r_log_step);
+    size_t cap = std::max(log_cap, 1);
+    CK(cudaMalloc(&e->r_log_err, B * cap * 8));
+    CK(cudaMalloc(&e->r_log_energy, B * cap * 8));
+    CK(cudaMalloc(&e->r_log_slot, B * cap * 4));
+    CK(cudaMalloc(&e->r_log_step, B * cap * 4));
+    e->r_log_cap = (int)cap;
+  }
+  if (e->r_islast) cudaFree(e->r_islast);
+  e->r_islast = nullptr;
+  CK(cudaMalloc(&e->r_islast, std::max(n_dts, 1) * 4));
+  if (n_dts > 0) CK(cudaMemcpy(e->r_islast, is_last_value, n_dts * 4, cudaMemcpyHostToDevice));
+  const int gb = (int)((B + 255) / 256);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_slot, (int)B, 0);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_iter, (int)B, 0);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_step, (int)B, 0);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_active, (int)B, (n_dts > 0 && max_iterations > 0) ? 1 : 0);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_conv, (int)B, 0);
+  fill_int_kernel<<<gb, 256, 0, e->stream>>>(e->r_nchecks, (int)B, 0);
+  CK(cudaGetLastError());
+
+  RunState st{};
+  st.batch = e->batch;
+  st.m_edges = e->m;
+  st.n_dts = n_dts;
+  st.max_iter = max_iterations;
+  st.log_cap = e->r_log_cap;
+  st.tol = tol;
+  st.slot = e->r_slot;
+  st.iter = e->r_iter;
+  st.step = e->r_step;
+  st.active = e->r_active;
+  st.conv = e->r_conv;
+  st.nchecks = e->r_nchecks;
+  st.log_slot = e->r_log_slot;
+  st.log_step = e->r_log_step;
+  st.nactive = e->r_nactive;
+  st.is_last = e->r_islast;
+  st.log_err = e->r_log_err;
+  st.log_energy = e->r_log_energy;
+  st.edge_err = e->edge_err;
+  st.energy = e->energy;
+
+  const long long max_global = (long long)n_dts * max_iterations;
+  const int poll = 4;
+  bool any = (n_dts > 0 && max_iterations > 0);
+  for (long long it = 0; it < max_global && any; ++it) {
+    int rc = one_sweep(e, 0, e->r_slot, e->r_active);
+    if (rc) return rc;
+    if (it >= 2) {
+      // energy at check iterations (self-gated per point on r_iter); no point checks before its 3rd sweep
+      rc = ensure_static_descs(e);
+      if (rc) return rc;
+      rc = energy_launch(e, e->r_iter, e->r_active);
+      if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(e->r_nactive, 0, 4, e->stream));
+    run_state_kernel<<<gb, 256, 0, e->stream>>>(st);
+    CK(cudaGetLastError());
+    e->launches++;
+    if ((it + 1) % poll == 0 || it + 1 == max_global) {
+      CK(cudaMemcpyAsync(e->h_nactive, e->r_nactive, 4, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      any = (*e->h_nactive > 0);
+    }
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  // download per-point results
+  if (n_checks) CK(cudaMemcpy(n_checks, e->r_nchecks, B * 4, cudaMemcpyDeviceToHost));
+  if (converged) CK(cudaMemcpy(converged, e->r_conv, B * 4, cudaMemcpyDeviceToHost));
+  if (total_sweeps) CK(cudaMemcpy(total_sweeps, e->r_step, B * 4, cudaMemcpyDeviceToHost));
+  if (log_cap > 0) {
+    size_t w = (size_t)log_cap, pitch = (size_t)e->r_log_cap;
+    if (log_error) CK(cudaMemcpy2D(log_error, w * 8, e->r_log_err, pitch * 8, w * 8, B, cudaMemcpyDeviceToHost));
+    if (log_energy) CK(cudaMemcpy2D(log_energy, w * 8, e->r_log_energy, pitch * 8, w * 8, B, cudaMemcpyDeviceToHost));
+    if (log_slot) CK(cudaMemcpy2D(log_slot, w * 4, e->r_log_slot, pitch * 4, w * 4, B, cudaMemcpyDeviceToHost));
+    if (log_step) CK(cudaMemcpy2D(log_step, w * 4, e->r_log_step, pitch * 4, w * 4, B, cudaMemcpyDeviceToHost));
+  }
+  return TNSU_OK;
+}
+
+void *tnsu_stream(tnsu_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int tnsu_synchronize(tnsu_engine *e) {
+  if (!e) return TNSU_E_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return TNSU_OK;
+}
+
+int64_t tnsu_launch_count(const tnsu_engine *e) { return e ? e->launches : -1; }
+
+int tnsu_debug_edge(tnsu_engine *e, int slot, int edge, int point, void *l_i, void *l_j, double *sigma, int32_t *info) {
+  if (!e) return TNSU_E_ARG;
+  if (edge < 0 || edge >= e->m || point < 0 || point >= e->batch) return fail(e, TNSU_E_ARG, "debug_edge: bad argument");
+  if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "debug_edge: gates of slot %d not set", slot);
+  CK(cudaSetDevice(e->device));
+  // A single edge out of sweep order: plan from the current dims, then only that edge's descriptor is
+  // valid if no earlier edge of the plan changes a dimension it sees (true in steady state).
+  if (!e->plan_valid) {
+    int rc = plan_sweep(e);
+    if (rc) return rc;
+  }
+  if (!e->plan_steady) return fail(e, TNSU_E_STATE, "debug_edge needs steady bond dimensions");
+  int rc = (e->dtype == TNSU_C128) ? run_levels<cplx>(e, slot, nullptr, nullptr, edge, point)
+                                   : run_levels<double>(e, slot, nullptr, nullptr, edge, point);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(e->stream));
+  int h_info[16];
+  CK(cudaMemcpy(h_info, e->dbg_info, sizeof h_info, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 16; ++i) info[i] = h_info[i];
+  const size_t ni = (size_t)h_info[0] * h_info[1], nj = (size_t)h_info[2] * h_info[3];
+  const int nc = std::min(h_info[4], h_info[5]);
+  std::vector<char> tmp(std::max(ni, nj) * e->ssz);
+  auto fetch = [&](void *dst, void *src, size_t cnt) -> int {
+    CK(cudaMemcpy(tmp.data(), src, cnt * e->ssz, cudaMemcpyDeviceToHost));
+    double *o = (double *)dst;
+    if (e->dtype == TNSU_C128)
+      memcpy(o, tmp.data(), cnt * 16);
+    else
+      for (size_t i = 0; i < cnt; ++i) {
+        o[2 * i] = ((double *)tmp.data())[i];
+        o[2 * i + 1] = 0.0;
+      }
+    return TNSU_OK;
+  };
+  if ((rc = fetch(l_i, e->dbg_li, ni))) return rc;
+  if ((rc = fetch(l_j, e->dbg_lj, nj))) return rc;
+  CK(cudaMemcpy(sigma, e->dbg_sigma, nc * 8, cudaMemcpyDeviceToHost));
+  return TNSU_OK;
+}
+
+}  // extern "C"

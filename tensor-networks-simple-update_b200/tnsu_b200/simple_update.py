@@ -1,0 +1,399 @@
+"""`SimpleUpdate` / `SimpleUpdateBatch`: the drop-in algorithm surface over the B200 engine.
+
+`SimpleUpdate` keeps the constructor, methods, attributes, logger keys and print-outs of the
+reference's `tnsu.simple_update.SimpleUpdate` (src/tnsu/simple_update.py:12-667).  What stays on
+the host is exactly what must stay there for bit-parity of the inputs: the two-site Hamiltonian
+(numpy kron, :420-454) and the gate expm(-dt H) (scipy, :470-473) — computed once per (edge, dt)
+instead of once per edge per sweep.  Everything else — weight absorption, QR reduction, gate
+application, truncated SVD, renormalisation, the RDM contractions and the run loop's convergence
+logic — executes in libtnsu_b200.so on the GPU.  There is no CPU fallback.
+
+`SimpleUpdateBatch` is the superset the reference lacks (SURVEY.md §8b "Superset allowed"): many
+independent points (fields, couplings, angles, seeds) of one lattice advance in the same launches.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import linalg
+
+from .engine import Engine
+from .tensor_network import TensorNetwork
+
+_NO_TRUNCATION = 1 << 20  # d_max=None in the reference means "keep everything"
+
+
+def _per_point(value, n_points, name):
+    """Broadcast a shared parameter or validate a per-point list."""
+    if isinstance(value, _PerPoint):
+        if len(value.items) != n_points:
+            raise ValueError(f"{name}: {len(value.items)} per-point values for {n_points} points")
+        return list(value.items)
+    return [value] * n_points
+
+
+class _PerPoint:
+    """Marks a constructor argument of SimpleUpdateBatch as 'one value per point'."""
+
+    def __init__(self, items):
+        self.items = list(items)
+
+
+def per_point(items) -> _PerPoint:
+    return _PerPoint(items)
+
+
+class SimpleUpdateBatch:
+    """Simple Update on `len(tensor_networks)` independent networks of one structure matrix and one shape.
+
+    j_ij, h_k, hamiltonian and dts may be shared or wrapped in `per_point([...])`; s_i, s_j, s_k are shared.
+    All points use dt schedules of the same LENGTH (values may differ)."""
+
+    def __init__(self, tensor_networks, j_ij, h_k, s_i, s_j, s_k, dts, d_max=2, max_iterations=1000,
+                 convergence_error=1e-6, hamiltonian=None, device=0, stream=None):
+        self.tensor_networks = list(tensor_networks)
+        self.n_points = len(self.tensor_networks)
+        if self.n_points == 0:
+            raise ValueError("at least one tensor network is required")
+        tn0 = self.tensor_networks[0]
+        for tn in self.tensor_networks[1:]:
+            if not np.array_equal(tn.structure_matrix, tn0.structure_matrix):
+                raise ValueError("all networks of a batch must share one structure matrix")
+        self.structure_matrix = np.asarray(tn0.structure_matrix)
+        self.s_i, self.s_j, self.s_k = s_i, s_j, s_k
+        self.j_ij = _per_point(j_ij, self.n_points, "j_ij")
+        self.h_k = _per_point(h_k, self.n_points, "h_k")
+        self.hamiltonian = _per_point(hamiltonian, self.n_points, "hamiltonian")
+        self.dts = _per_point(list(dts) if not isinstance(dts, _PerPoint) else dts, self.n_points, "dts")
+        if len({len(x) for x in self.dts}) != 1:
+            raise ValueError("all points must use dt schedules of the same length")
+        self.d_max = d_max
+        self.max_iterations = max_iterations
+        self.convergence_error = convergence_error
+        self.device = device
+        self.stream = stream
+        self._engine: Engine | None = None
+        self._gates_key = None
+        self._hams_uploaded = False
+        self.results = None
+
+    # ------------------------------------------------------------------ host-side operators
+    @property
+    def spin_dims(self):
+        return self.s_i[0].shape[0], self.s_j[0].shape[0]
+
+    def coordination(self, ek):
+        rows = np.nonzero(self.structure_matrix[:, ek])[0]
+        return (int(np.sum(self.structure_matrix[rows[0], :] > 0)), int(np.sum(self.structure_matrix[rows[1], :] > 0)))
+
+    def edge_hamiltonian(self, point, ek, i_neighbors=None, j_neighbors=None):
+        """d^2 x d^2 complex Hamiltonian of one edge, same arithmetic as the reference (:420-454)."""
+        if self.hamiltonian[point] is not None:
+            return self.hamiltonian[point]
+        if i_neighbors is None:
+            i_neighbors, j_neighbors = self.coordination(ek)
+        di, dj = self.spin_dims
+        interaction = np.zeros((di * dj, di * dj), dtype=complex)
+        for a, b in zip(self.s_i, self.s_j):
+            interaction += np.kron(a, b)
+        field_i = np.zeros((di * dj, di * dj), dtype=complex)
+        field_j = np.zeros((di * dj, di * dj), dtype=complex)
+        for s in self.s_k:
+            field_i += np.kron(s, np.eye(dj))
+            field_j += np.kron(np.eye(di), s)
+        return self.j_ij[point][ek] * interaction + self.h_k[point] * (field_i / i_neighbors + field_j / j_neighbors)
+
+    def _all_hamiltonians(self):
+        m = self.structure_matrix.shape[1]
+        d2 = self.spin_dims[0] * self.spin_dims[1]
+        out = np.empty((self.n_points, m, d2, d2), dtype=complex)
+        cache = {}
+        for p in range(self.n_points):
+            for ek in range(m):
+                shared = self.hamiltonian[p] is not None
+                key = (id(self.hamiltonian[p]),) if shared else (id(self.j_ij[p]), self.j_ij[p][ek], self.h_k[p],
+                                                                  self.coordination(ek))
+                if key not in cache:
+                    cache[key] = np.asarray(self.edge_hamiltonian(p, ek), dtype=complex)
+                out[p, ek] = cache[key]
+        return out
+
+    def _gates(self, hams, dts_of_point):
+        """expm(-dt H) per (point, edge); identical matrices are exponentiated once."""
+        out = np.empty_like(hams)
+        cache = {}
+        for p in range(hams.shape[0]):
+            for ek in range(hams.shape[1]):
+                key = (hams[p, ek].tobytes(), complex(dts_of_point[p]))
+                if key not in cache:
+                    cache[key] = linalg.expm(-dts_of_point[p] * hams[p, ek])
+                out[p, ek] = cache[key]
+        return out
+
+    # ------------------------------------------------------------------ engine lifecycle
+    def _current_dims(self):
+        tn = self.tensor_networks[0]
+        return [len(w) for w in tn.weights]
+
+    def _wants_complex(self, extra=()):
+        for tn in self.tensor_networks:
+            for t in tn.tensors:
+                if np.iscomplexobj(t) and np.any(np.imag(t) != 0.0):
+                    return True
+        for a in extra:
+            if np.iscomplexobj(a) and np.any(np.imag(a) != 0.0):
+                return True
+        return False
+
+    def _ensure_engine(self, extra_ops=()):
+        """Create (or re-create when shapes / dtype changed) the engine and upload the host state."""
+        dims = self._current_dims()
+        hams = self._all_hamiltonians()
+        need_complex = self._wants_complex((hams,) + tuple(extra_ops)) or any(
+            np.iscomplexobj(np.asarray(x)) and np.any(np.imag(np.asarray(x)) != 0.0) for dts in self.dts for x in dts)
+        d_max = _NO_TRUNCATION if self.d_max is None else int(self.d_max)
+        eng = self._engine
+        if (eng is None or list(eng.edge_dims) != dims or eng.d_max != d_max or (need_complex and not eng.complex)):
+            if eng is not None:
+                eng.close()
+            eng = Engine(self.structure_matrix, self.tensor_networks[0].tensors[0].shape[0], dims, d_max,
+                         need_complex, batch=self.n_points, device=self.device, stream=self.stream)
+            eng.reserve_gate_slots(len(self.dts[0]) + 1)
+            self._engine = eng
+            self._gates_key = None
+            self._hams_uploaded = False
+        self._hams = hams
+        if not self._hams_uploaded:
+            eng.set_hamiltonians(hams)
+            self._hams_uploaded = True
+        self.upload_state()
+        return eng
+
+    def upload_state(self):
+        eng = self._engine
+        n, m = self.structure_matrix.shape
+        for t in range(n):
+            stacked = np.stack([np.asarray(tn.tensors[t]) for tn in self.tensor_networks])
+            eng.set_tensor(t, stacked if eng.complex else np.real(stacked))
+        for e in range(m):
+            eng.set_weights(e, np.stack([np.asarray(tn.weights[e], dtype=float) for tn in self.tensor_networks]))
+
+    def download_state(self):
+        """Write the device state back into the TensorNetwork objects (complex128 tensors, as the
+        reference leaves them after an update, :435 + :483)."""
+        eng = self._engine
+        n, m = self.structure_matrix.shape
+        for t in range(n):
+            vals = eng.get_tensor(t)
+            for p, tn in enumerate(self.tensor_networks):
+                tn.tensors[t] = np.array(vals[p], dtype=np.complex128)
+        for e in range(m):
+            vals = eng.get_weights(e)
+            for p, tn in enumerate(self.tensor_networks):
+                tn.weights[e] = np.array(vals[p])
+
+    def _set_schedule_gates(self):
+        key = ("schedule", tuple(tuple(complex(x) for x in d) for d in self.dts))
+        if self._gates_key == key:
+            return
+        n_dts = len(self.dts[0])
+        for s in range(n_dts):
+            self._engine.set_gates(s, self._gates(self._hams, [d[s] for d in self.dts]))
+        self._gates_key = key
+
+    # ------------------------------------------------------------------ public API
+    def simple_update(self, dt=None, n_sweeps=1):
+        """n_sweeps sweeps over all edges with time step dt (shared or per_point)."""
+        dts = _per_point(0.1 if dt is None else dt, self.n_points, "dt")
+        gates = self._gates(self._all_hamiltonians(), dts)
+        eng = self._ensure_engine((gates,))
+        scratch = len(self.dts[0])
+        eng.set_gates(scratch, gates)
+        eng.sweep(scratch, n_sweeps)
+        self.download_state()
+
+    def run(self):
+        """SimpleUpdate.run() for every point.  Returns a list of per-point logger dicts."""
+        eng = self._ensure_engine()
+        self._set_schedule_gates()
+        n_dts = len(self.dts[0])
+        # the reference compares dt VALUES with dts[-1] (:176); with per-point schedules use point 0's pattern
+        is_last = [int(self.dts[0][s] == self.dts[0][-1]) for s in range(n_dts)]
+        res = eng.run(is_last, self.max_iterations, self.convergence_error)
+        self.download_state()
+        loggers = []
+        for p in range(self.n_points):
+            k = int(res["n_checks"][p])
+            loggers.append({
+                "error": [float(x) for x in res["log_error"][p, :k]],
+                "dt": [self.dts[p][int(s)] for s in res["log_slot"][p, :k]],
+                "iteration": [int(x) for x in res["log_step"][p, :k]],
+                "energy": [float(x) for x in res["log_energy"][p, :k]],
+                "converged": bool(res["converged"][p]),
+                "sweeps": int(res["sweeps"][p]),
+            })
+        self.results = loggers
+        return loggers
+
+    def energy_per_site(self) -> np.ndarray:
+        return self._ensure_engine().energy()
+
+    def tensor_pair_rdm(self, common_edge) -> np.ndarray:
+        return self._ensure_engine().pair_rdm(common_edge)
+
+    def tensor_rdm(self, tensor_index) -> np.ndarray:
+        return self._ensure_engine().site_rdm(tensor_index)
+
+    def pair_expectation_per_site(self, operator) -> np.ndarray:
+        op = np.asarray(operator, dtype=complex)
+        return np.real(self._ensure_engine((op,)).pair_expectation_per_site(op))
+
+    def expectation_per_site(self, operator) -> np.ndarray:
+        op = np.asarray(operator, dtype=complex)
+        return np.real(self._ensure_engine().expectation_per_site(op))
+
+    @property
+    def engine(self) -> Engine:
+        return self._engine if self._engine is not None else self._ensure_engine()
+
+
+class SimpleUpdate:
+    """Drop-in for tnsu.simple_update.SimpleUpdate (reference :12-667), one network, GPU engine underneath."""
+
+    def __init__(self, tensor_network: TensorNetwork, j_ij: list, h_k: float, s_i: list, s_j: list, s_k: list,
+                 dts: list, d_max: int = 2, max_iterations: int = 1000, convergence_error: float = 1e-6,
+                 log_energy: bool = False, print_process: bool = True, hamiltonian=None, device: int = 0):
+        self.tensor_network = tensor_network
+        self.j_ij, self.s_i, self.s_j, self.h_k, self.s_k = j_ij, s_i, s_j, h_k, s_k
+        self.d_max = d_max
+        self.dts = dts
+        self.max_iterations = max_iterations
+        self.convergence_error = convergence_error
+        self.dt = 0.1
+        self.old_weights = None
+        self.hamiltonian = hamiltonian
+        self.logger = {"error": [], "dt": [], "iteration": [], "energy": [], "j_ij": j_ij, "h_k": h_k, "d_max": d_max,
+                       "max_iterations": max_iterations, "convergence_error": convergence_error}
+        self.log_energy = log_energy
+        self.print_process = print_process
+        self.converged = False
+        self.device = device
+        self._batch: SimpleUpdateBatch | None = None
+
+    # ---- reference properties (:95-105) ----
+    @property
+    def tensors(self):
+        return self.tensor_network.tensors
+
+    @property
+    def weights(self):
+        return self.tensor_network.weights
+
+    @property
+    def structure_matrix(self):
+        return self.tensor_network.structure_matrix
+
+    def _impl(self) -> SimpleUpdateBatch:
+        """The one-point batch behind this object; parameters are re-read on every call because the
+        reference reads self.j_ij / self.h_k / self.d_max / ... at call time."""
+        b = self._batch
+        if b is None or b.tensor_networks[0] is not self.tensor_network:
+            b = SimpleUpdateBatch([self.tensor_network], self.j_ij, self.h_k, self.s_i, self.s_j, self.s_k,
+                                  list(self.dts), self.d_max, self.max_iterations, self.convergence_error,
+                                  self.hamiltonian, device=self.device)
+            self._batch = b
+        b.j_ij, b.h_k, b.hamiltonian = [self.j_ij], [self.h_k], [self.hamiltonian]
+        b.s_i, b.s_j, b.s_k = self.s_i, self.s_j, self.s_k
+        if [list(self.dts)] != b.dts:
+            b.dts = [list(self.dts)]
+            b._gates_key = None
+            if b._engine is not None and b._engine.n_slots != len(self.dts) + 1:
+                b._engine.reserve_gate_slots(len(self.dts) + 1)
+        b.d_max, b.max_iterations, b.convergence_error = self.d_max, self.max_iterations, self.convergence_error
+        b._hams_uploaded = False  # Hamiltonian parameters may have changed; the upload is tiny
+        b._gates_key = None
+        return b
+
+    # ---- run loop (:107-194) ----
+    def run(self):
+        error = np.inf
+        impl = self._impl()
+        if len(self.dts) > 0 and self.max_iterations > 0:
+            log = impl.run()[0]
+            for err, dt, it, en in zip(log["error"], log["dt"], log["iteration"], log["energy"]):
+                self.logger["error"].append(err)
+                self.logger["dt"].append(dt)
+                self.logger["iteration"].append(it)
+                if self.log_energy:
+                    self.logger["energy"].append(en)
+                if self.print_process:
+                    print("| D max: {:2d} | dt: {:8.6f} | iteration: {:5d}/{:5d} | convergence error: {:13.10f} | "
+                          "energy per-site: {: 16.11f} | iteration time: {:5.1f} sec | tot time:{:7.1f} min".format(
+                              self.d_max, np.real(dt), it, self.max_iterations, err, np.round(en, 10), 0.0, 0.0))
+            if log["error"]:
+                error = log["error"][-1]
+            if log["dt"]:
+                self.dt = log["dt"][-1]
+            self.converged = log["converged"]
+        self.tensor_network.su_logger = self.logger
+        if self.converged:
+            print("==> Simple Update converged. final error is {:4.10f} < {:4.10f}.".format(error, self.convergence_error))
+        else:
+            print("==> Simple Update did not converged. final error is {:4.10f} > {:4.10f}.".format(
+                error, self.convergence_error))
+
+    def compute_convergence_error(self):
+        """max_e ||lambda_e(old) - lambda_e(new)||_2 (:196-206).  With explicit old_weights the host lists are
+        compared as the reference does; otherwise the value the kernels accumulated during the last sweep."""
+        if self.old_weights is not None:
+            return np.max([np.sqrt(np.sum(np.square(o - n))) for o, n in zip(self.old_weights, self.weights)])
+        return float(self._impl().engine.sweep_error()[0])
+
+    def simple_update(self):
+        """One sweep over all edges with the current self.dt (:208-296)."""
+        self._impl().simple_update(self.dt, 1)
+
+    # ---- structure lookups (:298-338) ----
+    def get_tensors(self, edge: int):
+        rows = np.nonzero(self.structure_matrix[:, edge])[0]
+        axes = self.structure_matrix[rows, edge]
+        return ({"tensor": np.copy(self.tensors[rows[0]]), "index": rows[0], "dim": axes[0]},
+                {"tensor": np.copy(self.tensors[rows[1]]), "index": rows[1], "dim": axes[1]})
+
+    def get_other_edges(self, tensor_idx, edge_to_delete):
+        edges = np.nonzero(self.structure_matrix[tensor_idx, :])[0]
+        edges = edges[edges != edge_to_delete]
+        return {"edges": edges, "dims": self.structure_matrix[tensor_idx, edges]}
+
+    def get_edges(self, tensor_idx: int):
+        return self.tensor_network.get_edges(tensor_idx=tensor_idx)
+
+    def get_hamiltonian(self, i_neighbors, j_neighbors, ek):
+        return self._impl().edge_hamiltonian(0, ek, i_neighbors, j_neighbors)
+
+    # ---- observables (:498-661) ----
+    def tensor_rdm(self, tensor_index):
+        return self._impl().tensor_rdm(tensor_index)[0]
+
+    def tensor_pair_rdm(self, common_edge):
+        return self._impl().tensor_pair_rdm(common_edge)[0]
+
+    def tensor_expectation(self, tensor_index, operator):
+        return np.trace(np.matmul(self.tensor_rdm(tensor_index), operator))
+
+    def tensor_pair_expectation(self, common_edge, operator):
+        return np.einsum("ijkl,ijkl->", self.tensor_pair_rdm(common_edge), operator)
+
+    def energy_per_site(self):
+        return float(self._impl().energy_per_site()[0])
+
+    def pair_expectation_per_site(self, operator):
+        return float(self._impl().pair_expectation_per_site(operator)[0])
+
+    def expectation_per_site(self, operator):
+        return float(self._impl().expectation_per_site(operator)[0])
+
+    def absorb_weights(self, tensor, edges_dims):
+        return self.tensor_network.absorb_weights(tensor=tensor, edges_dims=edges_dims)
+
+    def absorb_inverse_weights(self, tensor, edges_dims):
+        return self.tensor_network.absorb_inverse_weights(tensor=tensor, edges_dims=edges_dims)
