@@ -248,6 +248,7 @@ def run_gpu_arm(args):
     ms = ev0.elapsed_time(ev1)
     kern_ms, n_launch = eng.last_sweep_kernel_ms()
     gpu_launches = eng.launch_count - launches0
+    prof = eng.profile_sweep(0)  # one extra sweep with events between the kernel classes (not part of `value`)
 
     # ---- end to end through the API with host buffers ----
     def e2e_step():
@@ -309,6 +310,7 @@ def run_gpu_arm(args):
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cpu_edges} edge updates of one peps D=8 network, numpy/scipy oracle, 1 BLAS thread"},
             "clocks": clocks.summary(),
+            "kernel_ms_per_sweep": prof,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -88,6 +88,7 @@ DEV void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(
 // ---------------------------------------------------------------------------------------------
 struct SideDesc {
   void *base;               // device pointer of tensor storage: point b at base + b*point_stride scalars
+  void *ybase;              // scratch of the same geometry: the Householder reflectors Y^H (K x N) between K1 and K3
   long long point_stride;   // capacity in scalars between consecutive points
   int tensor;               // tensor index
   int nlegs;                // z

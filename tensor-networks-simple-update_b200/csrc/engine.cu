@@ -21,10 +21,9 @@ static thread_local std::string g_create_error;
 struct LevelCfg {
   int mm_t = 0;      // MMAX template (8/16/32)
   int ncols = 1;     // NCOLS template
-  bool cluster = false;
-  int nt = 32;       // threads per side
-  int ldm = 0, lda = 0, ldv = 0;
-  EdgeSmem sm{};
+  int nt = 32;       // threads per side CTA
+  int lda = 0, ldv = 0, nr_max = 0;
+  int smem_lq = 0, smem_svd = 0, smem_rc = 0;
 };
 
 struct tnsu_engine {
@@ -47,6 +46,14 @@ struct tnsu_engine {
   int dcap = 1;
   // device state
   std::vector<void *> tens;
+  std::vector<void *> ybuf;               // reflector scratch, same geometry as tens
+  void *small = nullptr;                  // per-item small matrices
+  size_t small_bytes = 0;
+  int ldm = 1;                            // leading dimension of every small matrix in the current plan
+  int max_level_size = 1;
+  double prof_ms[3] = {0, 0, 0};
+  bool profile = false;
+  cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
   double *weights = nullptr, *tscale = nullptr, *edge_err = nullptr, *energy = nullptr;
   void *gates = nullptr, *hams = nullptr, *op_buf = nullptr;
   int n_slots = 0;
@@ -69,7 +76,6 @@ struct tnsu_engine {
   int r_log_cap = 0;
   int *h_nactive = nullptr;  // pinned
   // debug buffers
-  void *dbg_li = nullptr, *dbg_lj = nullptr;
   double *dbg_sigma = nullptr;
   int *dbg_info = nullptr;
   // bookkeeping
@@ -101,43 +107,6 @@ static int fail(tnsu_engine *e, int code, const char *fmt, ...) {
 
 static int align16(int x) { return (x + 15) & ~15; }
 
-static EdgeSmem make_edge_smem(size_t ssz, int mmax, int ldm, int lda, int ldv, int ncmax, int dcap, int d4,
-                               bool cluster) {
-  EdgeSmem s{};
-  int o = 0;
-  auto take = [&](int bytes) {
-    int at = o;
-    o = align16(o + bytes);
-    return at;
-  };
-  s.o_wleg = take(TNSU_MAX_LEGS * dcap * 8);
-  s.o_rowin = take(mmax * 8);
-  s.o_rowout = take(mmax * 8);
-  s.o_red = take(2 * TNSU_MAX_WARPS * mmax * (int)ssz);
-  s.o_colk = take(2 * mmax * (int)ssz);
-  s.o_mat_a = take(ldm * ldm * (int)ssz);
-  s.o_mat_b = take(ldm * ldm * (int)ssz);
-  s.o_mat_c = take(ldm * ldm * (int)ssz);
-  s.o_mat_d = take(ldm * ldm * (int)ssz);
-  s.o_tau = take(mmax * 8);
-  s.o_nred = take(TNSU_MAX_WARPS * 8);
-  s.side_bytes = o;
-  s.o_shared = cluster ? s.side_bytes : 2 * s.side_bytes;
-  o = 0;
-  s.o_svd_a = take(lda * ncmax * (int)ssz);
-  s.o_svd_v = take(ldv * ncmax * (int)ssz);
-  s.o_sig = take(TNSU_MAX_SVD * 8);
-  s.o_order = take(TNSU_MAX_SVD * 4);
-  s.o_lam_old = take(dcap * 8);
-  s.o_lam_new = take(dcap * 8);
-  s.o_flag = take(16);
-  s.o_gate = take(d4 * (int)ssz);
-  s.o_peer_l = take(cluster ? ldm * ldm * (int)ssz : 16);
-  s.o_peer_rt = take(cluster ? ldm * ldm * (int)ssz : 16);
-  s.total_bytes = s.o_shared + o;
-  return s;
-}
-
 static int max_threads(bool cplx_, int mm, int nc) {
   int doubles = mm * nc * (cplx_ ? 2 : 1);
   return doubles > 48 ? 256 : 512;
@@ -160,6 +129,7 @@ static int plan_sweep(tnsu_engine *e) {
       const std::vector<int> &legs = e->t_edges[t];
       sd.tensor = t;
       sd.base = e->tens[t];
+      sd.ybase = e->ybuf[t];
       sd.point_stride = e->cap[t];
       sd.nlegs = (int)legs.size();
       sd.bond_leg = e->edges[ek].leg[sd_i];
@@ -201,6 +171,16 @@ static int plan_sweep(tnsu_engine *e) {
   // per-level kernel configuration
   e->cfgs.assign(e->level_edges.size(), LevelCfg{});
   const bool cx = e->dtype == TNSU_C128;
+  int ldm_all = 1;
+  for (int ek = 0; ek < e->m; ++ek)
+    for (int s = 0; s < 2; ++s) {
+      const SideDesc &sd = e->h_descs[ek].s[s];
+      ldm_all = std::max(ldm_all, std::max(sd.M, std::max(sd.Mout, sd.K)));
+    }
+  if (ldm_all > TNSU_MAX_M)
+    return fail(e, TNSU_E_UNSUPPORTED, "bond matrix has %d rows (d*D); this build holds at most %d", ldm_all, TNSU_MAX_M);
+  e->ldm = ldm_all | 1;
+  const int ssz = (int)e->ssz;
   for (size_t lv = 0; lv < e->level_edges.size(); ++lv) {
     int maxM = 1, maxN = 1, maxnr = 1, maxnc = 1;
     for (int ek : e->level_edges[lv]) {
@@ -214,33 +194,46 @@ static int plan_sweep(tnsu_engine *e) {
     }
     LevelCfg c;
     c.mm_t = maxM <= 8 ? 8 : (maxM <= 16 ? 16 : 32);
-    if (maxM > TNSU_MAX_M)
-      return fail(e, TNSU_E_UNSUPPORTED, "bond matrix has %d rows (d*D); this build holds at most %d", maxM, TNSU_MAX_M);
     if (maxnr > TNSU_MAX_SVD)
       return fail(e, TNSU_E_UNSUPPORTED, "theta has %d rows; this build holds at most %d", maxnr, TNSU_MAX_SVD);
     bool ok = false;
-    const bool modes[4] = {false, false, true, true};
-    const int ncs[4] = {1, 2, 1, 2};
-    for (int o = 0; o < 4 && !ok; ++o) {
-      int nt = ((maxN + ncs[o] - 1) / ncs[o] + 31) & ~31;
-      int lim = max_threads(cx, c.mm_t, ncs[o]);
-      if (!modes[o]) lim /= 2;
-      if (nt > lim || nt > TNSU_MAX_WARPS * 32) continue;
-      c.cluster = modes[o];
-      c.ncols = ncs[o];
+    const int order2[2] = {2, 1}, order1[2] = {1, 2};
+    const int *ncs = (maxN > 128) ? order2 : order1;  // two columns per thread once the matrix is wide
+    for (int o = 0; o < 2 && !ok; ++o) {
+      const int nc = ncs[o];
+      if (cx && c.mm_t == 32 && nc == 2) continue;  // not instantiated: 256 data registers per thread
+      int nt = ((maxN + nc - 1) / nc + 31) & ~31;
+      if (nt > max_threads(cx, c.mm_t, nc) || nt > TNSU_MAX_WARPS * 32) continue;
+      c.ncols = nc;
       c.nt = nt;
-      c.ldm = maxM | 1;
-      c.lda = maxnr | 1;
-      c.ldv = maxnc | 1;
-      c.sm = make_edge_smem(e->ssz, c.mm_t, c.ldm, c.lda, c.ldv, maxnc, e->dcap, e->d4, c.cluster);
-      if (c.sm.total_bytes > SMEM_LIMIT) continue;
       ok = true;
     }
     if (!ok)
       return fail(e, TNSU_E_UNSUPPORTED,
-                  "no kernel variant holds a %d x %d bond matrix (%s) on chip; reduce the bond dimension",
+                  "no kernel variant holds a %d x %d bond matrix (%s) in registers; reduce the bond dimension",
                   maxM, maxN, cx ? "complex128" : "float64");
+    c.lda = maxnr | 1;
+    c.nr_max = maxnr;
+    c.ldv = maxnc | 1;
+    const int ldm2 = e->ldm * e->ldm;
+    c.smem_lq = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + (2 * TNSU_MAX_WARPS * c.mm_t + 2 * c.mm_t + 4 * ldm2) * ssz +
+                c.mm_t * 8 + 64;
+    c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + c.ldv * c.ldv) * ssz + 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
+    c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
+    if (std::max(c.smem_lq, std::max(c.smem_svd, c.smem_rc)) > SMEM_LIMIT)
+      return fail(e, TNSU_E_UNSUPPORTED, "edge update needs %d bytes of shared memory", std::max(c.smem_lq, c.smem_svd));
     e->cfgs[lv] = c;
+  }
+  {
+    size_t need = (size_t)e->batch * e->max_level_size * SM_COUNT * e->ldm * e->ldm * e->ssz;
+    if (need > e->small_bytes) {
+      cudaStreamSynchronize(e->stream);
+      if (e->small) cudaFree(e->small);
+      e->small = nullptr;
+      cudaError_t st2 = cudaMalloc(&e->small, need);
+      if (st2 != cudaSuccess) return fail(e, TNSU_E_CUDA, "scratch allocation of %zu bytes: %s", need, cudaGetErrorString(st2));
+      e->small_bytes = need;
+    }
   }
   cudaError_t st = cudaMemcpyAsync(e->d_descs, e->h_descs.data(), sizeof(EdgeDesc) * e->m, cudaMemcpyHostToDevice,
                                    e->stream);
@@ -255,40 +248,36 @@ static int plan_sweep(tnsu_engine *e) {
 // ---------------------------------------------------------------------------------------------
 // the kernel variants are instantiated in edge_inst.cu (one translation unit per scalar type and MMAX,
 // compiled in parallel); here they are only declared
-#define TNSU_EXTERN_VARIANT(S, MM, NC, CL) \
-  extern template cudaError_t launch_edge_variant<S, MM, NC, CL>(const EdgeLaunch<S> &, int, int, int, cudaStream_t);
-#define TNSU_EXTERN_MM(S, MM)            \
-  TNSU_EXTERN_VARIANT(S, MM, 1, false) \
-  TNSU_EXTERN_VARIANT(S, MM, 1, true)  \
-  TNSU_EXTERN_VARIANT(S, MM, 2, false) \
-  TNSU_EXTERN_VARIANT(S, MM, 2, true)
-TNSU_EXTERN_MM(double, 8)
-TNSU_EXTERN_MM(double, 16)
-TNSU_EXTERN_MM(double, 32)
-TNSU_EXTERN_MM(cplx, 8)
-TNSU_EXTERN_MM(cplx, 16)
-TNSU_EXTERN_VARIANT(cplx, 32, 1, false)
-TNSU_EXTERN_VARIANT(cplx, 32, 1, true)
+#define TNSU_EXTERN_VARIANT(S, MM, NC)                                                                   \
+  extern template cudaError_t launch_lq_variant<S, MM, NC>(const EdgeLaunch<S> &, int, cudaStream_t);    \
+  extern template cudaError_t launch_rc_variant<S, MM, NC>(const EdgeLaunch<S> &, int, cudaStream_t);
+TNSU_EXTERN_VARIANT(double, 8, 1)
+TNSU_EXTERN_VARIANT(double, 8, 2)
+TNSU_EXTERN_VARIANT(double, 16, 1)
+TNSU_EXTERN_VARIANT(double, 16, 2)
+TNSU_EXTERN_VARIANT(double, 32, 1)
+TNSU_EXTERN_VARIANT(double, 32, 2)
+TNSU_EXTERN_VARIANT(cplx, 8, 1)
+TNSU_EXTERN_VARIANT(cplx, 8, 2)
+TNSU_EXTERN_VARIANT(cplx, 16, 1)
+TNSU_EXTERN_VARIANT(cplx, 16, 2)
+TNSU_EXTERN_VARIANT(cplx, 32, 1)
+extern template cudaError_t launch_svd<double>(const EdgeLaunch<double> &, int, cudaStream_t);
+extern template cudaError_t launch_svd<cplx>(const EdgeLaunch<cplx> &, int, cudaStream_t);
 
 template <typename S>
-static cudaError_t launch_edge(const LevelCfg &c, const EdgeLaunch<S> &p, int n_work, cudaStream_t st) {
-  const int threads = c.cluster ? c.nt : 2 * c.nt;
-  const int smem = c.sm.total_bytes;
-#define VAR(MM, NC, CL) \
-  if (c.mm_t == MM && c.ncols == NC && c.cluster == CL) return launch_edge_variant<S, MM, NC, CL>(p, n_work, threads, smem, st);
-  VAR(8, 1, false)
-  VAR(8, 2, false)
-  VAR(8, 1, true)
-  VAR(8, 2, true)
-  VAR(16, 1, false)
-  VAR(16, 2, false)
-  VAR(16, 1, true)
-  VAR(16, 2, true)
-  VAR(32, 1, false)
-  VAR(32, 1, true)
+static cudaError_t launch_side_kernel(bool recompose, const LevelCfg &c, const EdgeLaunch<S> &p, int n_items,
+                                      cudaStream_t st) {
+#define VAR(MM, NC)                         \
+  if (c.mm_t == MM && c.ncols == NC)        \
+    return recompose ? launch_rc_variant<S, MM, NC>(p, n_items, st) : launch_lq_variant<S, MM, NC>(p, n_items, st);
+  VAR(8, 1)
+  VAR(8, 2)
+  VAR(16, 1)
+  VAR(16, 2)
+  VAR(32, 1)
   if constexpr (sizeof(S) == 8) {
-    VAR(32, 2, false)
-    VAR(32, 2, true)
+    VAR(32, 2)
   }
 #undef VAR
   return cudaErrorInvalidConfiguration;
@@ -303,44 +292,61 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.descs = e->d_descs;
     p.level_edges = e->d_level_edges + e->level_off[lv];
     p.n_level_edges = (int)e->level_edges[lv].size();
-    int batch = e->batch;
     if (only_edge >= 0) {
       if (e->level[only_edge] != (int)lv) continue;
       p.level_edges = e->d_all_edges + only_edge;
       p.n_level_edges = 1;
     }
-    p.batch = batch;
+    p.batch = e->batch;
     p.m_edges = e->m;
     p.dcap = e->dcap;
     p.d4 = e->d4;
+    p.n_tensors = e->n;
     p.weights = e->weights;
     p.tscale = e->tscale;
-    p.n_tensors = e->n;
     p.gates = (const S *)e->gates;
     p.gate_slot_stride = (long long)e->batch * e->m * e->d4;
     p.point_slot = point_slot;
     p.fixed_slot = fixed_slot;
     p.active = active;
     p.edge_err = e->edge_err;
-    p.nt_side = c.nt;
-    p.ldm = c.ldm;
+    p.small = (S *)e->small;
+    p.ldm = e->ldm;
     p.lda = c.lda;
     p.ldv = c.ldv;
-    p.sm = c.sm;
+    p.nr_max = c.nr_max;
+    p.nt = c.nt;
+    p.smem_lq = c.smem_lq;
+    p.smem_svd = c.smem_svd;
+    p.smem_rc = c.smem_rc;
     p.dbg_info = nullptr;
     if (dbg_point >= 0) {
-      p.dbg_li = (S *)e->dbg_li;
-      p.dbg_lj = (S *)e->dbg_lj;
       p.dbg_sigma = e->dbg_sigma;
       p.dbg_info = e->dbg_info;
       p.dbg_point = dbg_point;
     }
-    cudaError_t st = launch_edge<S>(c, p, batch * p.n_level_edges, e->stream);
+    const int n_items = e->batch * p.n_level_edges;
+    cudaError_t st = cudaSuccess;
+    if (e->profile) cudaEventRecord(e->pev[0], e->stream);
+    st = launch_side_kernel<S>(false, c, p, n_items, e->stream);
+    if (e->profile) cudaEventRecord(e->pev[1], e->stream);
+    if (st == cudaSuccess) st = launch_svd<S>(p, n_items, e->stream);
+    if (e->profile) cudaEventRecord(e->pev[2], e->stream);
+    if (st == cudaSuccess) st = launch_side_kernel<S>(true, c, p, n_items, e->stream);
+    if (e->profile) {
+      cudaEventRecord(e->pev[3], e->stream);
+      cudaEventSynchronize(e->pev[3]);
+      for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->pev[k], e->pev[k + 1]);
+        e->prof_ms[k] += ms;
+      }
+    }
     if (st != cudaSuccess)
-      return fail(e, TNSU_E_CUDA, "edge kernel launch (level %zu, MM=%d NC=%d cluster=%d nt=%d smem=%d): %s", lv,
-                  c.mm_t, c.ncols, (int)c.cluster, c.nt, c.sm.total_bytes, cudaGetErrorString(st));
-    e->launches++;
-    e->last_n++;
+      return fail(e, TNSU_E_CUDA, "edge kernel launch (level %zu, MM=%d NC=%d nt=%d smem=%d/%d/%d): %s", lv, c.mm_t,
+                  c.ncols, c.nt, c.smem_lq, c.smem_svd, c.smem_rc, cudaGetErrorString(st));
+    e->launches += 3;
+    e->last_n += 3;
   }
   return TNSU_OK;
 }
@@ -561,10 +567,14 @@ int tnsu_destroy(tnsu_engine *e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (void *p : e->tens) cudaFree(p);
+  for (void *p : e->ybuf) cudaFree(p);
+  if (e->small) cudaFree(e->small);
+  for (int k = 0; k < 4; ++k)
+    if (e->pev[k]) cudaEventDestroy(e->pev[k]);
   void *ptrs[] = {e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
                   e->rdm_buf, e->site_buf, e->d_descs, e->d_level_edges, e->d_all_edges, e->d_site, e->r_slot,
                   e->r_iter, e->r_step, e->r_active, e->r_conv, e->r_nchecks, e->r_log_slot, e->r_log_step,
-                  e->r_nactive, e->r_islast, e->r_log_err, e->r_log_energy, e->dbg_li, e->dbg_lj, e->dbg_sigma,
+                  e->r_nactive, e->r_islast, e->r_log_err, e->r_log_energy, e->dbg_sigma,
                   e->dbg_info};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -713,10 +723,14 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->own_stream = true;
   }
   e->tens.assign(n, nullptr);
+  e->ybuf.assign(n, nullptr);
   for (int t = 0; t < n; ++t) {
     CKC(cudaMalloc(&e->tens[t], (size_t)batch * e->cap[t] * e->ssz));
     CKC(cudaMemsetAsync(e->tens[t], 0, (size_t)batch * e->cap[t] * e->ssz, e->stream));
+    CKC(cudaMalloc(&e->ybuf[t], (size_t)batch * e->cap[t] * e->ssz));
   }
+  for (auto &lv : e->level_edges) e->max_level_size = std::max(e->max_level_size, (int)lv.size());
+  for (int k = 0; k < 4; ++k) CKC(cudaEventCreate(&e->pev[k]));
   size_t B = batch;
   CKC(cudaMalloc(&e->weights, B * m * e->dcap * 8));
   CKC(cudaMemsetAsync(e->weights, 0, B * m * e->dcap * 8, e->stream));
@@ -753,8 +767,6 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   CKC(cudaMalloc(&e->r_nchecks, B * 4));
   CKC(cudaMalloc(&e->r_nactive, 4));
   CKC(cudaMallocHost(&e->h_nactive, 4));
-  CKC(cudaMalloc(&e->dbg_li, 64 * 64 * 16));
-  CKC(cudaMalloc(&e->dbg_lj, 64 * 64 * 16));
   CKC(cudaMalloc(&e->dbg_sigma, 64 * 8));
   CKC(cudaMalloc(&e->dbg_info, 16 * 4));
   CKC(cudaEventCreate(&e->ev0));
@@ -914,6 +926,20 @@ int tnsu_sweep(tnsu_engine *e, int slot, int n_sweeps) {
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   e->timed = true;
+  return TNSU_OK;
+}
+
+int tnsu_profile_sweep(tnsu_engine *e, int slot, double *ms_out) {
+  if (!e) return TNSU_E_ARG;
+  if (!ms_out) return fail(e, TNSU_E_ARG, "profile_sweep: null");
+  if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "profile_sweep: gates of slot %d not set", slot);
+  CK(cudaSetDevice(e->device));
+  e->profile = true;
+  e->prof_ms[0] = e->prof_ms[1] = e->prof_ms[2] = 0.0;
+  int rc = one_sweep(e, slot, nullptr, nullptr);
+  e->profile = false;
+  if (rc) return rc;
+  for (int k = 0; k < 3; ++k) ms_out[k] = e->prof_ms[k];
   return TNSU_OK;
 }
 
@@ -1197,23 +1223,28 @@ int tnsu_debug_edge(tnsu_engine *e, int slot, int edge, int point, void *l_i, vo
   int h_info[16];
   CK(cudaMemcpy(h_info, e->dbg_info, sizeof h_info, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 16; ++i) info[i] = h_info[i];
-  const size_t ni = (size_t)h_info[0] * h_info[1], nj = (size_t)h_info[2] * h_info[3];
   const int nc = std::min(h_info[4], h_info[5]);
-  std::vector<char> tmp(std::max(ni, nj) * e->ssz);
-  auto fetch = [&](void *dst, void *src, size_t cnt) -> int {
-    CK(cudaMemcpy(tmp.data(), src, cnt * e->ssz, cudaMemcpyDeviceToHost));
+  const int ldm = e->ldm;
+  std::vector<char> tmp((size_t)ldm * ldm * e->ssz);
+  auto fetch = [&](void *dst, int which, int rows, int cols) -> int {
+    const char *src = (const char *)e->small + ((size_t)point * SM_COUNT + which) * ldm * ldm * e->ssz;
+    CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));
     double *o = (double *)dst;
-    if (e->dtype == TNSU_C128)
-      memcpy(o, tmp.data(), cnt * 16);
-    else
-      for (size_t i = 0; i < cnt; ++i) {
-        o[2 * i] = ((double *)tmp.data())[i];
-        o[2 * i + 1] = 0.0;
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        size_t si = (size_t)r * ldm + c, di = (size_t)r * cols + c;
+        if (e->dtype == TNSU_C128) {
+          o[2 * di] = ((double *)tmp.data())[2 * si];
+          o[2 * di + 1] = ((double *)tmp.data())[2 * si + 1];
+        } else {
+          o[2 * di] = ((double *)tmp.data())[si];
+          o[2 * di + 1] = 0.0;
+        }
       }
     return TNSU_OK;
   };
-  if ((rc = fetch(l_i, e->dbg_li, ni))) return rc;
-  if ((rc = fetch(l_j, e->dbg_lj, nj))) return rc;
+  if ((rc = fetch(l_i, SM_L0, h_info[0], h_info[1]))) return rc;
+  if ((rc = fetch(l_j, SM_L1, h_info[2], h_info[3]))) return rc;
   CK(cudaMemcpy(sigma, e->dbg_sigma, nc * 8, cudaMemcpyDeviceToHost));
   return TNSU_OK;
 }

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "tnsu_synchronize": (C.c_int, [_vp]),
     "tnsu_launch_count": (C.c_int64, [_vp]),
     "tnsu_last_sweep_kernel_ms": (C.c_int, [_vp, _f64p, _i32p]),
+    "tnsu_profile_sweep": (C.c_int, [_vp, C.c_int, _f64p]),
     "tnsu_debug_edge": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _f64p, _i32p]),
 }
 

@@ -191,6 +191,12 @@ class Engine:
         self._check(self._lib.tnsu_last_sweep_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_sweep(self, slot: int):
+        """One sweep with per-kernel-class CUDA-event timing: ms of (LQ, SVD, recompose) launches."""
+        ms = (C.c_double * 3)()
+        self._check(self._lib.tnsu_profile_sweep(self._h, int(slot), ms))
+        return {"lq": ms[0], "svd": ms[1], "recompose": ms[2]}
+
     def debug_edge(self, slot: int, edge: int, point: int = 0):
         li = np.zeros(64 * 64, dtype=np.complex128)
         lj = np.zeros(64 * 64, dtype=np.complex128)
@@ -202,8 +208,7 @@ class Engine:
         mi, ki, mj, kj, ni, nj, dnew, sweeps = (int(x) for x in info[:8])
         return dict(l_i=li[: mi * ki].reshape(mi, ki), l_j=lj[: mj * kj].reshape(mj, kj), sigma=sig[: min(ni, nj)],
                     d_new=dnew, svd_sweeps=sweeps,
-                    phase_cycles=dict(zip(["load", "lq", "wy", "theta", "svd", "extract", "store"],
-                                          (int(x) for x in info[8:15]))))
+                    phase_cycles=dict(zip(["theta", "jacobi", "extract"], (int(x) for x in info[8:11]))))
 
 
 def schedule_levels(structure_matrix) -> np.ndarray:

@@ -24,6 +24,8 @@ for name, cplx in (("peps_D8", False), ("peps_D8", True), ("tfi_D4", False), ("b
     for rep in range(2):
         dbg = eng.debug_edge(1, edge, 0)
     pc = dbg["phase_cycles"]
-    tot = sum(pc.values())
-    print(f"{name:10s} cplx={int(cplx)} edge {edge} svd_sweeps {dbg['svd_sweeps']:2d} total {tot:8d} cyc  " +
-          "  ".join(f"{k}={v}" for k, v in pc.items()), flush=True)
+    eng.sweep(1, 2)
+    prof = eng.profile_sweep(1)
+    print(f"{name:10s} cplx={int(cplx)} edge {edge} svd_sweeps {dbg['svd_sweeps']:2d} K2 cycles " +
+          "  ".join(f"{k}={v}" for k, v in pc.items()) + "   sweep ms (B=1): " +
+          "  ".join(f"{k}={v:.3f}" for k, v in prof.items()), flush=True)
