@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into small text files that can be committed under profiles/.
+
+  python tools/ncu_summary.py launches <launches.csv>            -> per-kernel count / total / share table
+  python tools/ncu_summary.py full <report.ncu-rep> [regex]      -> key metrics of every profiled launch
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_sector_hit_rate.pct",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        k = re.sub(r"\(.*", "", r[ki])[:70]
+        agg[k][0] += 1
+        agg[k][1] += v
+    tot = sum(v for _, v in agg.values())
+    print(f"{'kernel':72s} {'n':>5s} {'total ms':>10s} {'share':>7s} {'avg us':>9s}")
+    for k, (n, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print(f"{k:72s} {n:5d} {v / 1e6:10.3f} {v / tot:7.3f} {v / n / 1e3:9.1f}")
+    print(f"{'TOTAL':72s} {sum(n for n, _ in agg.values()):5d} {tot / 1e6:10.3f}")
+
+
+def full(path, pattern=None):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if pattern and not re.search(pattern, name):
+            continue
+        print(f"== {name}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"   {k:72s} {r[i]:>18s} {units[i]}")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
