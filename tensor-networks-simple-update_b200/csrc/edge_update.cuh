@@ -65,6 +65,9 @@ struct EdgeLaunch {
   int lda, ldv;              // leading dimensions of the SVD work arrays (column-major)
   int nr_max;                // largest theta row count (after the rows >= cols transposition) in this launch
   int nt;                    // threads per side CTA (multiple of 32)
+  int svdw_np;               // register-resident warp SVD (svd_warp.cuh): processors (column pairs) per theta, 0 = not used
+  int svdw_rows;             // rows of [A] per lane = template R of svd_warp_kernel
+  int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
   int smem_lq, smem_svd, smem_rc;
   // debug dump (tnsu_debug_edge)
   double *dbg_sigma;

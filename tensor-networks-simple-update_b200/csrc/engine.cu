@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@ struct LevelCfg {
   int nt = 32;       // threads per side CTA
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
+  int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
 };
 
 struct tnsu_engine {
@@ -64,6 +66,7 @@ struct tnsu_engine {
   std::vector<EdgeDesc> h_descs;
   std::vector<int> post_dims;
   bool plan_valid = false, plan_steady = false;
+  bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
   std::vector<int> level_off;
@@ -220,6 +223,19 @@ static int plan_sweep(tnsu_engine *e) {
                 c.mm_t * 8 + 64;
     c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + c.ldv * c.ldv) * ssz + 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
     c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
+    // real thetas of at most 32 x 32 take the register-resident warp kernel (svd_warp.cuh)
+    if (!cx && maxnr <= 32 && !e->force_smem_svd) {
+      const int need = (maxnr + 1) / 2;
+      const int rt[6] = {2, 4, 6, 8, 12, 16};
+      for (int k = 0; k < 6; ++k)
+        if (rt[k] >= need) {
+          c.svdw_rows = rt[k];
+          break;
+        }
+      c.svdw_np = std::max(1, (maxnc + 1) / 2);
+      c.svdw_group_doubles = 2 * ldm2 + e->d4 + e->dcap + 2 * c.svdw_rows * 2 * c.svdw_np;
+      c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
+    }
     if (std::max(c.smem_lq, std::max(c.smem_svd, c.smem_rc)) > SMEM_LIMIT)
       return fail(e, TNSU_E_UNSUPPORTED, "edge update needs %d bytes of shared memory", std::max(c.smem_lq, c.smem_svd));
     e->cfgs[lv] = c;
@@ -283,6 +299,16 @@ static cudaError_t launch_side_kernel(bool recompose, const LevelCfg &c, const E
   return cudaErrorInvalidConfiguration;
 }
 
+cudaError_t launch_svd_warp_dispatch(const EdgeLaunch<double> &p, int n_items, cudaStream_t st);  // svdw_inst.cu
+
+template <typename S>
+static cudaError_t launch_k2(const LevelCfg &c, const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
+  if constexpr (sizeof(S) == 8) {
+    if (c.svdw_np > 0) return launch_svd_warp_dispatch(p, n_items, st);
+  }
+  return launch_svd<S>(p, n_items, st);
+}
+
 template <typename S>
 static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, const int *active, int only_edge,
                       int dbg_point) {
@@ -319,6 +345,9 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.smem_lq = c.smem_lq;
     p.smem_svd = c.smem_svd;
     p.smem_rc = c.smem_rc;
+    p.svdw_np = c.svdw_np;
+    p.svdw_rows = c.svdw_rows;
+    p.svdw_group_doubles = c.svdw_group_doubles;
     p.dbg_info = nullptr;
     if (dbg_point >= 0) {
       p.dbg_sigma = e->dbg_sigma;
@@ -330,7 +359,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     if (e->profile) cudaEventRecord(e->pev[0], e->stream);
     st = launch_side_kernel<S>(false, c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[1], e->stream);
-    if (st == cudaSuccess) st = launch_svd<S>(p, n_items, e->stream);
+    if (st == cudaSuccess) st = launch_k2<S>(c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[2], e->stream);
     if (st == cudaSuccess) st = launch_side_kernel<S>(true, c, p, n_items, e->stream);
     if (e->profile) {
@@ -637,6 +666,10 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
 
   e = new tnsu_engine();
   e->device = device;
+  {
+    const char *env = getenv("TNSU_SVD");
+    e->force_smem_svd = env && std::string(env) == "smem";
+  }
   e->n = n;
   e->m = m;
   e->d = d;

@@ -1,0 +1,357 @@
+// svd_warp.cuh — K2 for real float64 thetas of at most 32 x 32: one-sided Jacobi SVD with the whole
+// problem resident in REGISTERS of (part of) one warp.
+//
+// Replaces SimpleUpdate.truncation_svd (reference src/tnsu/simple_update.py:393-409, scipy gesdd) and the
+// theta contraction of time_evolution (:476-483) for the shapes of BASELINE configs 1, 2, 3 and 5.
+//
+// Layout.  A theta with nc (<= 2*NP) columns is handled by NP "processors" of 2 lanes each.  Processor k
+// holds two columns x, y of the stacked matrix [A; V] (A = theta or theta^H so that rows >= columns, V the
+// accumulated right rotations); lane half h holds rows h*R .. h*R+R-1 of both.  A warp holds 32/(2*NP)
+// independent thetas ("groups").  Nothing lives in shared memory during the iteration and there is no
+// block barrier: the only communication is
+//     - one shfl_xor(1) per dot product (the two row halves), and
+//     - an in-place cyclic shift of the x registers by one processor, alternately down and up,
+// which realises the odd-even transposition ordering: step A pairs positions (2k, 2k+1), step B pairs
+// (2k+1, 2k+2); every rotation writes its outputs swapped, so after n = 2*NP steps every pair of columns
+// has met exactly once (the classic odd-even Jacobi ordering, equivalent to the cyclic one).  The idle pair
+// of step B (positions n-1 and 0, sitting together in the last processor) gets the "rotation" (c,s)=(0,1),
+// which keeps both in place (one changes sign together with its V column: harmless).
+//
+// Cost per step and lane at R = 16: 64 SHFL + ~210 FP64 instructions -> FP64-pipe bound (measured B200
+// rates: 1 warp-SHFL / clk / SM, 1 warp-DFMA / 2 clk / SM sub-partition; profiles/r01_microbench_b200.txt).
+#pragma once
+#include "edge_update.cuh"
+
+#define SVDW_THREADS 128
+#define SVDW_MAX_SWEEPS 60
+
+template <int R>
+struct SvdwCols {
+  double xa[R], xv[R], ya[R], yv[R];
+};
+
+// one Jacobi step on the local pair (P, Q) with swapped outputs:  P <- s P + c Q,  Q <- c P - s Q
+template <int R>
+DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (&qv)[R], bool idle) {
+  double al0 = 0.0, al1 = 0.0, be0 = 0.0, be1 = 0.0, ga0 = 0.0, ga1 = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; r += 2) {
+    al0 = fma(pa[r], pa[r], al0);
+    be0 = fma(qa[r], qa[r], be0);
+    ga0 = fma(pa[r], qa[r], ga0);
+    if (r + 1 < R) {
+      al1 = fma(pa[r + 1], pa[r + 1], al1);
+      be1 = fma(qa[r + 1], qa[r + 1], be1);
+      ga1 = fma(pa[r + 1], qa[r + 1], ga1);
+    }
+  }
+  double al = al0 + al1, be = be0 + be1, ga = ga0 + ga1;
+  al += __shfl_xor_sync(0xffffffffu, al, 1);
+  be += __shfl_xor_sync(0xffffffffu, be, 1);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 1);
+  const double tol2 = 2.25e-30;  // (1.5e-15)^2, same threshold as the shared-memory kernel
+  const double g2 = ga * ga;
+  const bool rot = !idle && (g2 > tol2 * al * be) && (g2 > 0.0);
+  double c = 1.0, s = 0.0;
+  if (rot) {
+    const double delta = be - al;
+    const double inv_r = rsqrt(fma(delta, delta, 4.0 * g2));
+    const double c2 = fma(0.5 * fabs(delta), inv_r, 0.5);
+    const double inv_c = rsqrt(c2);
+    c = c2 * inv_c;
+    s = (delta < 0.0 ? -ga : ga) * inv_r * inv_c;
+  }
+  if (idle) {
+    c = 0.0;
+    s = 1.0;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double p0 = pa[r], q0 = qa[r];
+    pa[r] = fma(s, p0, c * q0);
+    qa[r] = fma(c, p0, -(s * q0));
+    const double p1 = pv[r], q1 = qv[r];
+    pv[r] = fma(s, p1, c * q1);
+    qv[r] = fma(c, p1, -(s * q1));
+  }
+  return rot;
+}
+
+template <int R>
+__global__ void __launch_bounds__(SVDW_THREADS, (R > 12) ? 3 : ((R > 8) ? 4 : 6)) svd_warp_kernel(const EdgeLaunch<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int NP = p.svdw_np;
+  const int G = 2 * NP;
+  const int gpw = 32 / G;  // groups per warp
+  const int grp = lane / G;
+  const int gl = lane - grp * G;
+  const int k = gl >> 1, h = gl & 1;
+  const int n_items = p.batch * p.n_level_edges;
+  const int item = (blockIdx.x * (SVDW_THREADS / 32) + warp) * gpw + grp;
+  bool valid = (grp < gpw) && (item < n_items);
+  int b = 0, ek = 0;
+  if (valid) {
+    b = item / p.n_level_edges;
+    ek = p.level_edges[item - b * p.n_level_edges];
+    if (p.active != nullptr && p.active[b] == 0) valid = false;
+  }
+  // whole-warp early out (no group of this warp has work)
+  if (!__any_sync(0xffffffffu, valid)) return;
+  const int ldm = p.ldm;
+  const int lda = 2 * R;
+
+  // per-group shared memory: Li | Lj | gate | lam_old | theta (column-major, lda x 2NP)
+  double *gs = (double *)smem_raw + (size_t)(warp * gpw + (grp < gpw ? grp : 0)) * p.svdw_group_doubles;
+  double *Li = gs;
+  double *Lj = Li + ldm * ldm;
+  double *gate_s = Lj + ldm * ldm;
+  double *lam_old = gate_s + p.d4;
+  double *th = lam_old + p.dcap;
+
+  int d = 1, Dk = 1, Dnew = 1, Ki = 1, Kj = 1, nr = 0, nc = 0;
+  bool transposed = false;
+  double *small = nullptr;
+  double *wpoint = nullptr;
+  if (valid) {
+    const EdgeDesc &ed = p.descs[ek];
+    d = ed.d;
+    Dk = ed.Dk;
+    Dnew = ed.Dnew;
+    Ki = ed.s[0].K;
+    Kj = ed.s[1].K;
+    const int ni = ed.ni, nj = ed.nj;
+    transposed = ni < nj;
+    nr = transposed ? nj : ni;
+    nc = transposed ? ni : nj;
+    small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+    wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
+    const double *gLi = small + SM_L0 * ldm * ldm, *gLj = small + SM_L1 * ldm * ldm;
+    const int Mi = ed.s[0].M, Mj = ed.s[1].M;
+    for (int idx = gl; idx < Mi * ldm; idx += G) Li[idx] = gLi[idx];
+    for (int idx = gl; idx < Mj * ldm; idx += G) Lj[idx] = gLj[idx];
+    const int slot = p.point_slot ? p.point_slot[b] : p.fixed_slot;
+    const double *gsrc = p.gates + (size_t)slot * p.gate_slot_stride + ((size_t)b * p.m_edges + ek) * p.d4;
+    for (int idx = gl; idx < p.d4; idx += G) gate_s[idx] = gsrc[idx];
+    for (int x = gl; x < Dk; x += G) lam_old[x] = wpoint[(size_t)ek * p.dcap + x];
+  }
+  __syncwarp();
+
+  // theta[(qi,i'),(j',qj)] = sum_{i,j,e} L_i[(i,e),qi] lam_e L_j[(j,e),qj] G[i,j,i',j']   (reference :476-483)
+  if (valid) {
+    for (int idx = gl; idx < Ki * Kj; idx += G) {
+      const int qi = idx / Kj, qj = idx - qi * Kj;
+      double x[TNSU_MAX_SPIN][TNSU_MAX_SPIN];
+#pragma unroll
+      for (int i = 0; i < TNSU_MAX_SPIN; ++i)
+#pragma unroll
+        for (int j = 0; j < TNSU_MAX_SPIN; ++j) {
+          double a = 0.0;
+          if (i < d && j < d)
+            for (int e = 0; e < Dk; ++e) a = fma(Li[(i * Dk + e) * ldm + qi] * lam_old[e], Lj[(j * Dk + e) * ldm + qj], a);
+          x[i][j] = a;
+        }
+#pragma unroll
+      for (int ip = 0; ip < TNSU_MAX_SPIN; ++ip)
+#pragma unroll
+        for (int jp = 0; jp < TNSU_MAX_SPIN; ++jp) {
+          if (ip < d && jp < d) {
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < TNSU_MAX_SPIN; ++i)
+#pragma unroll
+              for (int j = 0; j < TNSU_MAX_SPIN; ++j)
+                if (i < d && j < d) a = fma(x[i][j], gate_s[((i * d + j) * d + ip) * d + jp], a);
+            const int row = qi * d + ip, cl = jp * Kj + qj;
+            if (transposed)
+              th[(size_t)row * lda + cl] = a;  // A = theta^T
+            else
+              th[(size_t)cl * lda + row] = a;
+          }
+        }
+    }
+  }
+  __syncwarp();
+
+  // my two columns (2k, 2k+1) of [A; V], rows h*R .. h*R+R-1
+  double xa[R], xv[R], ya[R], yv[R];
+  {
+    const int c0 = 2 * k, c1 = 2 * k + 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int gr = h * R + r;
+      xa[r] = (valid && gr < nr && c0 < nc) ? th[(size_t)c0 * lda + gr] : 0.0;
+      ya[r] = (valid && gr < nr && c1 < nc) ? th[(size_t)c1 * lda + gr] : 0.0;
+      xv[r] = (valid && gr == c0 && c0 < nc) ? 1.0 : 0.0;
+      yv[r] = (valid && gr == c1 && c1 < nc) ? 1.0 : 0.0;
+    }
+  }
+
+  // source lanes of the cyclic x shifts (invalid / surplus lanes shuffle with themselves)
+  const int base = grp * G;
+  const bool in_group = grp < gpw;
+  const int src_next = in_group ? base + 2 * ((k + 1 == NP) ? 0 : k + 1) + h : lane;  // layout A -> B
+  const int src_prev = in_group ? base + 2 * ((k == 0) ? NP - 1 : k - 1) + h : lane;  // layout B -> A
+  const bool last = (k == NP - 1);
+
+  int sweeps = 0;
+  for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
+    bool rotated = false;
+    for (int st = 0; st < NP; ++st) {
+      // step A: pairs (x_k, y_k)
+      rotated |= svdw_rotate<R>(xa, xv, ya, yv, false);
+      // layout A -> B: x_k <- x_{k+1}  (the last processor receives position 0)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        xa[r] = __shfl_sync(0xffffffffu, xa[r], src_next);
+        xv[r] = __shfl_sync(0xffffffffu, xv[r], src_next);
+      }
+      // step B: pairs (y_k, x_k) = positions (2k+1, 2k+2); the last processor idles
+      rotated |= svdw_rotate<R>(ya, yv, xa, xv, last);
+      // layout B -> A
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        xa[r] = __shfl_sync(0xffffffffu, xa[r], src_prev);
+        xv[r] = __shfl_sync(0xffffffffu, xv[r], src_prev);
+      }
+    }
+    if (!__any_sync(0xffffffffu, rotated)) {
+      ++sweeps;
+      break;
+    }
+  }
+
+  // singular values = column norms; dummy (padding) columns have V == 0 and sort last
+  double sx, sy;
+  {
+    double nx = 0.0, ny = 0.0, vx = 0.0, vy = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      nx = fma(xa[r], xa[r], nx);
+      ny = fma(ya[r], ya[r], ny);
+      vx = fma(xv[r], xv[r], vx);
+      vy = fma(yv[r], yv[r], vy);
+    }
+    nx += __shfl_xor_sync(0xffffffffu, nx, 1);
+    ny += __shfl_xor_sync(0xffffffffu, ny, 1);
+    vx += __shfl_xor_sync(0xffffffffu, vx, 1);
+    vy += __shfl_xor_sync(0xffffffffu, vy, 1);
+    sx = (vx > 0.5) ? sqrt(nx) : -1.0;
+    sy = (vy > 0.5) ? sqrt(ny) : -1.0;
+  }
+  // rank of my columns in descending order (ties: lower (processor, slot) first)
+  int rank_x = 0, rank_y = 0;
+  for (int j = 0; j < NP; ++j) {
+    const int src = in_group ? base + 2 * j + h : lane;
+    const double ox = __shfl_sync(0xffffffffu, sx, src);
+    const double oy = __shfl_sync(0xffffffffu, sy, src);
+    rank_x += (ox > sx || (ox == sx && 2 * j < 2 * k)) ? 1 : 0;
+    rank_x += (oy > sx || (oy == sx && 2 * j + 1 < 2 * k)) ? 1 : 0;
+    rank_y += (ox > sy || (ox == sy && 2 * j < 2 * k + 1)) ? 1 : 0;
+    rank_y += (oy > sy || (oy == sy && 2 * j + 1 < 2 * k + 1)) ? 1 : 0;
+  }
+  const bool sel_x = valid && rank_x < Dnew;
+  const bool sel_y = valid && rank_y < Dnew;
+  double tot = 0.0;
+  {
+    const double mine = (sel_x ? sx : 0.0) + (sel_y ? sy : 0.0);
+    for (int j = 0; j < NP; ++j) tot += __shfl_sync(0xffffffffu, mine, in_group ? base + 2 * j : lane);
+  }
+  // lambda' = s / sum(s)  (reference :296) and this edge's convergence error (:196-206)
+  double e2 = 0.0;
+  if (sel_x) {
+    const double ln = sx / tot;
+    if (h == 0) wpoint[(size_t)ek * p.dcap + rank_x] = ln;
+    const double df = ln - lam_old[rank_x];
+    e2 += df * df;
+  }
+  if (sel_y) {
+    const double ln = sy / tot;
+    if (h == 0) wpoint[(size_t)ek * p.dcap + rank_y] = ln;
+    const double df = ln - lam_old[rank_y];
+    e2 += df * df;
+  }
+  double err2 = 0.0;
+  for (int j = 0; j < NP; ++j) err2 += __shfl_sync(0xffffffffu, e2, in_group ? base + 2 * j : lane);
+  if (valid && gl == 0) p.edge_err[(size_t)b * p.m_edges + ek] = (Dnew == Dk) ? sqrt(err2) : nan("");
+
+  // r~_i[(i',x'),qi] = U[(qi,i'),x'],   r~_j[(j',x'),qj] = V^T[x',(j',qj)]     (reference :268-271)
+  if (valid) {
+    double *rt_i = small + SM_R0 * ldm * ldm, *rt_j = small + SM_R1 * ldm * ldm;
+    const int ncols_v = nc;  // V is nc x nc
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const bool sel = which ? sel_y : sel_x;
+      const int xp = which ? rank_y : rank_x;
+      const double sv = which ? sy : sx;
+      if (sel) {
+        const double isv = sv > 0.0 ? 1.0 / sv : 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int gr = h * R + r;
+          const double av = (which ? ya[r] : xa[r]) * isv;  // U (or V of theta when transposed) row gr
+          const double vv = which ? yv[r] : xv[r];
+          // non-transposed: A rows are theta rows (qi,i'), V rows are theta columns (j',qj); transposed: the reverse
+          const double row_val = transposed ? vv : av;  // value attached to theta ROW index gr
+          const double col_val = transposed ? av : vv;  // value attached to theta COLUMN index gr
+          const int n_rowidx = transposed ? ncols_v : nr;
+          const int n_colidx = transposed ? nr : ncols_v;
+          if (gr < n_rowidx) {
+            const int qi = gr / d, ip = gr - qi * d;
+            rt_i[(ip * Dnew + xp) * ldm + qi] = row_val;
+          }
+          if (gr < n_colidx) {
+            const int jp = gr / Kj, qj = gr - jp * Kj;
+            rt_j[(jp * Dnew + xp) * ldm + qj] = col_val;
+          }
+        }
+      }
+    }
+    if (p.dbg_info != nullptr && b == p.dbg_point) {
+      if (sel_x && h == 0) p.dbg_sigma[rank_x] = sx;
+      if (sel_y && h == 0) p.dbg_sigma[rank_y] = sy;
+      if (!sel_x && h == 0 && rank_x < TNSU_MAX_SVD && sx >= 0.0) p.dbg_sigma[rank_x] = sx;
+      if (!sel_y && h == 0 && rank_y < TNSU_MAX_SVD && sy >= 0.0) p.dbg_sigma[rank_y] = sy;
+      if (gl == 0) {
+        const EdgeDesc &ed = p.descs[ek];
+        p.dbg_info[0] = ed.s[0].M;
+        p.dbg_info[1] = Ki;
+        p.dbg_info[2] = ed.s[1].M;
+        p.dbg_info[3] = Kj;
+        p.dbg_info[4] = ed.ni;
+        p.dbg_info[5] = ed.nj;
+        p.dbg_info[6] = Dnew;
+        p.dbg_info[7] = sweeps;
+        p.dbg_info[8] = p.dbg_info[9] = p.dbg_info[10] = 0;
+      }
+    }
+  }
+}
+
+template <int R>
+cudaError_t launch_svd_warp_r(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
+  auto kern = svd_warp_kernel<R>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+    if (s != cudaSuccess) return s;
+    attr_done = true;
+  }
+  const int gpw = 32 / (2 * p.svdw_np);
+  const int per_cta = (SVDW_THREADS / 32) * gpw;
+  const int smem = per_cta * p.svdw_group_doubles * 8;
+  kern<<<(n_items + per_cta - 1) / per_cta, SVDW_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+// rows per lane -> kernel variant; p.svdw_rows = ceil(nr_max / 2)
+inline cudaError_t launch_svd_warp(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
+  const int r = p.svdw_rows;
+  if (r <= 2) return launch_svd_warp_r<2>(p, n_items, st);
+  if (r <= 4) return launch_svd_warp_r<4>(p, n_items, st);
+  if (r <= 6) return launch_svd_warp_r<6>(p, n_items, st);
+  if (r <= 8) return launch_svd_warp_r<8>(p, n_items, st);
+  if (r <= 12) return launch_svd_warp_r<12>(p, n_items, st);
+  return launch_svd_warp_r<16>(p, n_items, st);
+}
