@@ -5,8 +5,8 @@
 
 One "step" = one Simple-Update sweep (8 edge updates: absorb, QR reduction, gate, truncated SVD,
 renormalise) over a batch of B independent random-init networks of BASELINE.json configs[1]
-(d=2, virtual_dim = d_max = 8, j_ij=1, h_k=0, dt=0.1, seed b for network b).  B is chosen so the state
-(B x 4 tensors x 8192 float64 = B x 256 KiB) is far larger than the 126 MB L2.
+(d=2, virtual_dim = d_max = 8, j_ij=1, h_k=0, dt=0.1, seed b for network b).  B (default 8192 per GPU) is chosen
+so the state (B x 4 tensors x 8192 float64 = B x 256 KiB = 2 GiB) is far larger than the 126 MB L2.
 
   value  edge-updates/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks)
   e2e    the same metric through the public API with host buffers: every step uploads the B networks from
@@ -185,6 +185,73 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Metric 2: converged sweep points/s — BASELINE.json configs[2], the transverse-field Ising sweep
+# ------------------------------------------------------------------------------------------------
+def tfi_sweep(n_points, world, rank, local_rank, dist, torch):
+    """256-point TFI sweep on the "peps" cell (SURVEY.md 8d Metric 2): j_ij=-1, h_k=-linspace(0,4,n), d_max=4,
+    dts=[1e-1..1e-5], 200 iterations per dt, tol 1e-6, fresh random network per point (seed = point index);
+    full run() + energy + Mx + Mz per point.  Points are sharded round-robin over the ranks; the only collective is
+    the final all_gather of [energy, Mx, Mz, converged, sweeps] per point.  Strong scaling (total work fixed)."""
+    import tnsu_b200 as tnsu
+    from tnsu_b200 import sharding
+
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
+    fields = -np.linspace(0.0, 4.0, n_points)
+    mine = sharding.partition(n_points, world, rank)
+    nets = []
+    for k in mine:
+        np.random.seed(int(k))
+        nets.append(tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=4, spin_dim=2))
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    batch = tnsu.SimpleUpdateBatch(nets, [-1.0] * N_E, tnsu.per_point([float(fields[k]) for k in mine]), [pz], [pz], [px],
+                                   [0.1, 0.01, 0.001, 0.0001, 0.00001], d_max=4, max_iterations=200,
+                                   convergence_error=1e-6, device=local_rank)
+    logs = batch.run()
+    launches = batch.engine.launch_count
+    energy = batch.energy_per_site()
+    mx = batch.expectation_per_site(px)
+    mz = batch.expectation_per_site(pz)
+    local = np.stack([energy, mx, mz, np.array([float(lg["converged"]) for lg in logs]),
+                      np.array([float(lg["sweeps"]) for lg in logs])], axis=1)
+    full = sharding.gather_points(local, n_points, world, rank, device=torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.cpu()[0])
+    return {"metric": "converged sweep points/s (256-point TFI sweep, peps cell, D=4)", "value": n_points / dt,
+            "unit": "points/s", "seconds": dt, "n_points": n_points, "scaling": "strong",
+            "converged_points": int(full[:, 3].sum()), "total_sweeps": int(full[:, 4].sum()),
+            "edge_updates_per_s": float(full[:, 4].sum()) * N_E / dt, "gpu_launches_rank0": int(launches),
+            "energy_h0": float(full[0, 0]), "energy_h4": float(full[-1, 0]), "mx_h4": float(full[-1, 1]),
+            "what": "TensorNetwork construction excluded; gates (scipy expm), upload, run(), observables, gather included"}
+
+
+def tfi_sweep_cpu(n_sample, n_points):
+    """Oracle run() on `n_sample` of the sweep's points, one host core: seconds per point."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tnsu_oracle as orc
+    from tnsu_b200 import smc
+
+    smat = smc.infinite_structure_matrix_dict("peps")
+    pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
+    fields = -np.linspace(0.0, 4.0, n_points)
+    picks = np.linspace(0, n_points - 1, n_sample).astype(int)
+    t0 = time.perf_counter()
+    for k in picks:
+        np.random.seed(int(k))
+        tensors, weights = orc.random_network(smat, D, 4)
+        orc.run(tensors, weights, smat, orc.Model([-1.0] * N_E, float(fields[k]), [pz], [pz], [px]),
+                [0.1, 0.01, 0.001, 0.0001, 0.00001], 4, 200, 1e-6)
+    return (time.perf_counter() - t0) / n_sample, [int(k) for k in picks]
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -279,6 +346,11 @@ def run_gpu_arm(args):
     value = edges_per_step * args.steps / (ms * 1e-3)
     e2e_value = edges_per_step * args.e2e_steps / (e2e_ms * 1e-3)
 
+    sweep = None
+    if args.sweep_points > 0:
+        del eng
+        sweep = tfi_sweep(args.sweep_points, world, rank, local_rank, dist, torch)
+
     if rank == 0:
         pk, pk_kind = peaks()
         alg_launch = algorithmic_bytes_per_edge(sbytes) * batch * N_E * args.steps / n_launch
@@ -312,6 +384,12 @@ def run_gpu_arm(args):
             "clocks": clocks.summary(),
             "kernel_ms_per_sweep": prof,
         }
+        if sweep is not None:
+            if args.sweep_cpu_points > 0:
+                sec, picks = tfi_sweep_cpu(args.sweep_cpu_points, args.sweep_points)
+                sweep["cpu_baseline"] = {"value": 1.0 / sec, "unit": "points/s", "cores": 1, "kind": "port",
+                                         "sample": f"oracle run() of points {picks} of the sweep, 1 BLAS thread"}
+            line["sweep"] = sweep
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -322,7 +400,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="networks per GPU")
+    ap.add_argument("--batch", type=int, default=8192, help="networks per GPU")
+    ap.add_argument("--sweep-points", type=int, default=256, help="points of the TFI sweep (Metric 2); 0 skips it")
+    ap.add_argument("--sweep-cpu-points", type=int, default=2, help="points of the sweep the oracle runs for the CPU baseline")
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
