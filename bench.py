@@ -9,8 +9,8 @@ renormalise) over a batch of B independent random-init networks of BASELINE.json
 so the state (B x 4 tensors x 8192 float64 = B x 256 KiB = 2 GiB) is far larger than the 126 MB L2.
 
   value  edge-updates/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks)
-  e2e    the same metric through the public API with host buffers: every step uploads the B networks from
-         pinned host memory, runs the sweep, evaluates energy_per_site and reads energies + weights back
+  e2e    the same metric through the C ABI with host buffers: every step uploads the B networks from pinned host
+         memory, runs the sweep and reads the convergence error + weights back (chunks pipelined over two engines)
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
 
 --impl reference times the reference's algorithm on the host cores (the numpy/scipy oracle port; the
@@ -318,24 +318,56 @@ def run_gpu_arm(args):
     prof = eng.profile_sweep(0)  # one extra sweep with events between the kernel classes (not part of `value`)
 
     # ---- end to end through the API with host buffers ----
-    def e2e_step():
-        upload()
-        eng.sweep(0, 1)
-        energies = eng.energy()
-        for e in range(N_E):
-            out_w[e][...] = eng.get_weights(e)
-        return energies
+    # The batch is split over `e2e_chunks` engines (handles are independent: one stream each) driven by one host
+    # thread each, so the pinned-memory upload of one chunk overlaps the sweep of another.
+    del eng
+    n_ch = max(1, min(args.e2e_chunks, batch))
+    bounds = np.linspace(0, batch, n_ch + 1).astype(int)
+    parts = []
+    for c in range(n_ch):
+        lo, hi = int(bounds[c]), int(bounds[c + 1])
+        pe = tnsu.Engine(smat, D, [DIM] * N_E, DIM, cplx, batch=hi - lo, device=local_rank)
+        pe.reserve_gate_slots(1)
+        pe.set_gates(0, np.broadcast_to(gate, (hi - lo, N_E, 4, 4)))
+        pe.set_hamiltonians(np.broadcast_to(ham, (hi - lo, N_E, 4, 4)))
+        parts.append((pe, lo, hi))
+    out_e = pin(np.empty(batch))
 
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
+    # one lock per shared resource (PCIe upload, SM time): without them the chunk threads march in lockstep
+    # (all upload, then all sweep) and nothing overlaps; with them chunk c+1 uploads while chunk c sweeps
+    up_lock, gpu_lock = threading.Lock(), threading.Lock()
+
+    def e2e_chunk(pe, lo, hi, n_steps):
+        for _ in range(n_steps):
+            with up_lock:
+                for t in range(N_T):
+                    pe.set_tensor(t, host_t[t][lo:hi])
+                for e in range(N_E):
+                    pe.set_weights(e, host_w[lo:hi])
+            with gpu_lock:
+                pe.sweep(0, 1)
+                out_e[lo:hi] = pe.sweep_error()  # the step's result: convergence error (reference :196-206) + weights
+                for e in range(N_E):
+                    out_w[e][lo:hi] = pe.get_weights(e)
+
+    def e2e_run(n_steps):
+        threads = [threading.Thread(target=e2e_chunk, args=(pe, lo, hi, n_steps)) for pe, lo, hi in parts]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+
+    e2e_run(min(args.warmup, 2))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        energies = e2e_step()
+    e2e_run(args.e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    energies = out_e
     h2d = sum(t.nbytes for t in host_t) + N_E * host_w.nbytes
     d2h = energies.nbytes + sum(w.nbytes for w in out_w)
+    for pe, _, _ in parts:
+        pe.close()
 
     # ---- max over ranks ----
     times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -348,7 +380,6 @@ def run_gpu_arm(args):
 
     sweep = None
     if args.sweep_points > 0:
-        del eng
         sweep = tfi_sweep(args.sweep_points, world, rank, local_rank, dist, torch)
 
     if rank == 0:
@@ -372,7 +403,10 @@ def run_gpu_arm(args):
                        "arithmetic": "real float64 path (inputs with zero imaginary part)" if not cplx else "complex128 path",
                        "parallelism": f"points sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "what": "upload state (pinned) + 1 sweep + energy_per_site + download energies and weights"},
+                    "steps": args.e2e_steps, "chunks": n_ch,
+                    "what": "per step: upload all networks from pinned host memory + 1 sweep + download the convergence "
+                            "error and all weights, through the C ABI (the reference arm times the same sweep); the batch is split over `chunks` engines driven by "
+                            "one host thread each so uploads overlap sweeps"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
@@ -404,7 +438,8 @@ def main():
     ap.add_argument("--sweep-points", type=int, default=256, help="points of the TFI sweep (Metric 2); 0 skips it")
     ap.add_argument("--sweep-cpu-points", type=int, default=2, help="points of the sweep the oracle runs for the CPU baseline")
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
