@@ -65,6 +65,7 @@ struct EdgeLaunch {
   int lda, ldv;              // leading dimensions of the SVD work arrays (column-major)
   int nr_max;                // largest theta row count (after the rows >= cols transposition) in this launch
   int nt;                    // threads per side CTA (multiple of 32)
+  int lq_rolled;             // real float64: lq_rolled_kernel instead of lq_kernel
   int svdw_np;               // register-resident warp SVD (svd_warp.cuh): processors (column pairs) per theta, 0 = not used
   int svdw_rows;             // rows of [A] per lane = template R of svd_warp_kernel
   int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
@@ -335,6 +336,233 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   for (int idx = lt; idx < M * K; idx += nt) {
     const int r = idx / K, q = idx - r * K;
     gL[r * ldm + q] = matL[r * ldm + q];
+  }
+}
+
+// =============================================================================================
+// K1 (real float64), rolled form: the same Householder LQ with the step loop NOT unrolled over the rows.
+// After every block of U steps the register rows rotate by U, so inside a block the pivot row is a
+// compile-time register (row u), the rows still to be reduced follow it and the finished reflectors queue
+// up at the end of the register column — their inner products with the new reflector (compact-WY T factor)
+// fall out of the same reduction.  ~1 500 SASS instructions instead of ~10 000: the unrolled kernel spent
+// 18 % of its issue slots waiting for instruction fetch (profiles/r01a).  The per-step reduction of the MMAX
+// Gram values is a shared-memory transpose inside the warp (MMAX stores + MMAX loads per lane) followed by one
+// block barrier for the cross-warp sum.
+// =============================================================================================
+#define LQR_U 4       // steps per rotation block
+#define LQR_TPLD 33   // leading dimension of the per-warp transpose buffer
+
+template <int MMAX, int NCOLS>
+__global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq_rolled_kernel(const EdgeLaunch<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int item = blockIdx.x >> 1;
+  const int side = blockIdx.x & 1;
+  const int b = item / p.n_level_edges;
+  const int ek = p.level_edges[item - b * p.n_level_edges];
+  if (p.active != nullptr && p.active[b] == 0) return;
+
+  const EdgeDesc &ed = p.descs[ek];
+  const SideDesc &sd = ed.s[side];
+  const int nt = blockDim.x;
+  const int lt = threadIdx.x;
+  const int lane = lt & 31;
+  const int wl = lt >> 5;
+  const int nwarps = nt >> 5;
+  const int M = sd.M, N = sd.N, K = sd.K;
+  const int Dk = ed.Dk;
+  const int ldm = p.ldm;
+  constexpr int PARTS = 32 / MMAX;  // lanes sharing one register row in the transpose reduction
+  const int q = lane & (MMAX - 1);  // the register row this lane finalises
+  const int part = lane / MMAX;
+
+  // shared memory: wleg | rowin | red | colk | matL | matZ | matT | matY | tau | tp[nwarps]
+  double *wleg = (double *)smem_raw;                                  // [MAX_LEGS][dcap]
+  int *rowin = (int *)(wleg + TNSU_MAX_LEGS * p.dcap);                // [MMAX]
+  double *red = (double *)(rowin + MMAX + (MMAX & 1));                // [2][TNSU_MAX_WARPS][MMAX]
+  double *colk = red + 2 * TNSU_MAX_WARPS * MMAX;                     // [2][MMAX]
+  double *matL = colk + 2 * MMAX;                                     // L (M x K)
+  double *matZ = matL + ldm * ldm;                                    // Z (K x K), later S = Y1 T^H
+  double *matT = matZ + ldm * ldm;                                    // T (K x K)
+  double *matY = matT + ldm * ldm;                                    // first K columns of Y^H
+  double *tau_s = matY + ldm * ldm;                                   // [MMAX]
+  double *tp = tau_s + MMAX + (size_t)wl * MMAX * LQR_TPLD;           // [MMAX][LQR_TPLD] per warp
+
+  const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
+  for (int idx = lt; idx < sd.nlegs * p.dcap; idx += nt) {
+    int l = idx / p.dcap, x = idx - l * p.dcap;
+    wleg[idx] = (x < sd.dims[l]) ? wpoint[(size_t)sd.leg_edge[l] * p.dcap + x] : 1.0;
+  }
+  for (int r = lt; r < MMAX; r += nt) {
+    int s = r / Dk, x = r - s * Dk;
+    rowin[r] = (r < M) ? (int)(s * sd.in_stride_phys + x * sd.in_stride[sd.bond_leg]) : 0;
+  }
+  for (int idx = lt; idx < ldm * ldm; idx += nt) matL[idx] = 0.0;
+  __syncthreads();
+
+  // ---- load my columns, absorbing the environment weights ----
+  const double *tbase = (const double *)sd.base + (size_t)b * sd.point_stride;
+  const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
+  double col[NCOLS][MMAX];
+  bool cvalid[NCOLS];
+#pragma unroll
+  for (int j = 0; j < NCOLS; ++j) {
+    const int c = lt + j * nt;
+    cvalid[j] = c < N;
+    const ColInfo ci = decode_column(sd, cvalid[j] ? c : 0, wleg, p.dcap);
+    const double wc = ci.w * tsc;
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      double v = 0.0;
+      if (cvalid[j] && r < M) v = tbase[ci.in_off + rowin[r]] * wc;
+      col[j][r] = v;
+    }
+  }
+  double *ybase = (double *)sd.ybase + (size_t)b * sd.point_stride;
+
+  // ---- Householder steps, LQR_U per rotation block ----
+#pragma unroll 1
+  for (int kk0 = 0; kk0 < K; kk0 += LQR_U) {
+    static_for<0, LQR_U>([&](auto u_c) {
+      constexpr int u = decltype(u_c)::value;
+      const int kk = kk0 + u;
+      if (kk < K) {
+        const int buf = kk & 1;
+        if (lt == kk) {  // column kk is column j = 0 of thread kk (kk < 32 <= nt)
+#pragma unroll
+          for (int i = 0; i < MMAX; ++i) colk[buf * MMAX + i] = col[0][i];
+        }
+        // partial Gram row of the pivot (register row u) with every register row, over my columns c > kk
+        double pk[NCOLS];
+#pragma unroll
+        for (int j = 0; j < NCOLS; ++j) pk[j] = (j > 0 || lt > kk) ? col[j][u] : 0.0;
+#pragma unroll
+        for (int i = 0; i < MMAX; ++i) {
+          double a = col[0][i] * pk[0];
+#pragma unroll
+          for (int j = 1; j < NCOLS; ++j) a = fma(col[j][i], pk[j], a);
+          tp[i * LQR_TPLD + lane] = a;
+        }
+        __syncwarp();
+        // lane (q, part) sums MMAX of the 32 lane partials of register row q, then the parts combine
+        double g;
+        {
+          const double *src = tp + q * LQR_TPLD + part * MMAX;
+          double s0 = src[0], s1 = src[1], s2 = src[2], s3 = src[3];
+#pragma unroll
+          for (int i = 4; i < MMAX; i += 4) {
+            s0 += src[i];
+            s1 += src[i + 1];
+            s2 += src[i + 2];
+            s3 += src[i + 3];
+          }
+          g = (s0 + s1) + (s2 + s3);
+#pragma unroll
+          for (int m = MMAX; m < 32; m *= 2) g += __shfl_xor_sync(0xffffffffu, g, m);
+        }
+        if (lane < MMAX) red[(buf * TNSU_MAX_WARPS + wl) * MMAX + q] = g;
+        __syncthreads();
+        g = 0.0;
+        for (int w = 0; w < nwarps; ++w) g += red[(buf * TNSU_MAX_WARPS + w) * MMAX + q];
+        const double mycol = colk[buf * MMAX + q];
+        const double alpha = colk[buf * MMAX + u];
+        const double gk = __shfl_sync(0xffffffffu, g, u);
+        const double norm2 = fma(alpha, alpha, gk);
+        // roles of register row q: q < u reflector kk0+q; q == u pivot; u < q < MMAX-kk0 matrix row kk0+q;
+        // q >= MMAX-kk0 reflector q-(MMAX-kk0)
+        const int n_mat = MMAX - kk0;
+        const bool is_row = q > u && q < n_mat;
+        double w_l = 0.0, t_l = g, lnew = mycol, head = 0.0, lkk = 0.0, tau = 0.0;
+        if (norm2 > 0.0) {
+          const double norm = sqrt(norm2);
+          const double absa = fabs(alpha);
+          const double phase = (alpha < 0.0) ? -1.0 : 1.0;
+          const double uk = fma(phase, norm, alpha);  // head of the reflector u_k
+          tau = 1.0 / (norm * (norm + absa));
+          t_l = fma(mycol, uk, g);
+          w_l = t_l * tau;
+          lnew = fma(-w_l, uk, mycol);
+          head = uk;
+          lkk = -(phase * norm);
+        }
+        if (wl == 0 && lane < MMAX) {
+          if (q == u) {
+            matL[kk * ldm + kk] = lkk;
+            tau_s[kk] = tau;
+          } else if (is_row) {
+            if (kk0 + q < M) matL[(kk0 + q) * ldm + kk] = lnew;
+          } else {
+            const int ri = (q < u) ? kk0 + q : q - n_mat;
+            matZ[ri * ldm + kk] = t_l;
+          }
+        }
+        if (!is_row) w_l = 0.0;
+        // rank-1 update of the matrix rows still to be reduced (other register rows get w = 0)
+#pragma unroll
+        for (int i = u + 1; i < MMAX; ++i) {
+          const double wi = __shfl_sync(0xffffffffu, w_l, i);
+#pragma unroll
+          for (int j = 0; j < NCOLS; ++j) col[j][i] = fma(-wi, pk[j], col[j][i]);
+        }
+        // the pivot row becomes the stored reflector: row kk of Y^H goes to global (coalesced) and to matY
+#pragma unroll
+        for (int j = 0; j < NCOLS; ++j) {
+          const int c = lt + j * nt;
+          const double y = (c == kk) ? head : (c < kk ? 0.0 : col[j][u]);
+          col[j][u] = y;
+          if (cvalid[j]) ybase[(size_t)kk * N + c] = y;
+          if (j == 0 && lt < K) matY[kk * ldm + lt] = y;
+        }
+      }
+    });
+    // rotate the register rows by LQR_U: the block's reflectors move behind the matrix rows
+#pragma unroll
+    for (int j = 0; j < NCOLS; ++j) {
+      double t[LQR_U];
+#pragma unroll
+      for (int i = 0; i < LQR_U; ++i) t[i] = col[j][i];
+#pragma unroll
+      for (int i = 0; i + LQR_U < MMAX; ++i) col[j][i] = col[j][i + LQR_U];
+#pragma unroll
+      for (int i = 0; i < LQR_U; ++i) col[j][MMAX - LQR_U + i] = t[i];
+    }
+  }
+  __syncthreads();
+
+  // compact-WY factor: T[:k,k] = -tau_k T[:k,:k] Z[:k,k], T[k,k] = tau_k   (lane r holds row r)
+  if (wl == 0) {
+    double trow[MMAX];
+#pragma unroll
+    for (int k = 0; k < MMAX; ++k) trow[k] = 0.0;
+    static_for<0, MMAX>([&](auto kk_c) {
+      constexpr int kk = decltype(kk_c)::value;
+      if (kk < K) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < kk; ++j) a = fma(trow[j], matZ[j * ldm + kk], a);
+        const double tk = tau_s[kk];
+        trow[kk] = (lane < kk) ? -(a * tk) : (lane == kk ? tk : 0.0);
+      }
+    });
+    if (lane < K) {
+#pragma unroll
+      for (int k = 0; k < MMAX; ++k)
+        if (k < K) matT[lane * ldm + k] = trow[k];
+    }
+  }
+  __syncthreads();
+  // S[c][k'] = (Y1 T^H)[c][k'] = sum_k Yh[k][c] T[k'][k]  and L, both to the item's global scratch
+  double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+  double *gS = small + (SM_S0 + side) * ldm * ldm;
+  double *gL = small + (SM_L0 + side) * ldm * ldm;
+  for (int idx = lt; idx < K * K; idx += nt) {
+    const int c = idx / K, kp = idx - c * K;
+    double a = 0.0;
+    for (int k = kp; k <= c; ++k) a = fma(matY[k * ldm + c], matT[kp * ldm + k], a);
+    gS[c * ldm + kp] = a;
+  }
+  for (int idx = lt; idx < M * K; idx += nt) {
+    const int r = idx / K, qq = idx - r * K;
+    gL[r * ldm + qq] = matL[r * ldm + qq];
   }
 }
 
@@ -742,8 +970,24 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
 // ---------------------------------------------------------------------------------------------
 // host launchers (instantiated in edge_inst.cu)
 // ---------------------------------------------------------------------------------------------
+template <int MM, int NC>
+cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
+  auto kern = lq_rolled_kernel<MM, NC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+    if (s != cudaSuccess) return s;
+    attr_done = true;
+  }
+  kern<<<2 * n_items, p.nt, p.smem_lq, st>>>(p);
+  return cudaGetLastError();
+}
+
 template <typename S, int MM, int NC>
 cudaError_t launch_lq_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
+  if constexpr (std::is_same<S, double>::value) {
+    if (p.lq_rolled) return launch_lq_rolled<MM, NC>(p, n_items, st);
+  }
   auto kern = lq_kernel<S, MM, NC>;
   static bool attr_done = false;
   if (!attr_done) {

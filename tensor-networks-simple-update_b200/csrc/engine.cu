@@ -66,6 +66,7 @@ struct tnsu_engine {
   std::vector<EdgeDesc> h_descs;
   std::vector<int> post_dims;
   bool plan_valid = false, plan_steady = false;
+  bool force_unrolled_lq = false;         // TNSU_LQ=unrolled: keep the fully unrolled K1 (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
@@ -221,6 +222,7 @@ static int plan_sweep(tnsu_engine *e) {
     const int ldm2 = e->ldm * e->ldm;
     c.smem_lq = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + (2 * TNSU_MAX_WARPS * c.mm_t + 2 * c.mm_t + 4 * ldm2) * ssz +
                 c.mm_t * 8 + 64;
+    if (!cx) c.smem_lq += (c.nt / 32) * c.mm_t * 33 * 8;  // per-warp transpose buffers of lq_rolled_kernel
     c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + c.ldv * c.ldv) * ssz + 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
     c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
     // real thetas of at most 32 x 32 take the register-resident warp kernel (svd_warp.cuh)
@@ -345,6 +347,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.smem_lq = c.smem_lq;
     p.smem_svd = c.smem_svd;
     p.smem_rc = c.smem_rc;
+    p.lq_rolled = (!e->force_unrolled_lq && e->dtype == TNSU_F64) ? 1 : 0;
     p.svdw_np = c.svdw_np;
     p.svdw_rows = c.svdw_rows;
     p.svdw_group_doubles = c.svdw_group_doubles;
@@ -669,6 +672,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   {
     const char *env = getenv("TNSU_SVD");
     e->force_smem_svd = env && std::string(env) == "smem";
+    env = getenv("TNSU_LQ");
+    e->force_unrolled_lq = env && std::string(env) == "unrolled";
   }
   e->n = n;
   e->m = m;
