@@ -69,6 +69,8 @@ struct EdgeLaunch {
   int svdw_np;               // register-resident warp SVD (svd_warp.cuh): processors (column pairs) per theta, 0 = not used
   int svdw_rows;             // rows of [A] per lane = template R of svd_warp_kernel
   int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
+  int svdw_precond;          // pivoted-QR preconditioner before the Jacobi iteration
+  int svdw_ldt;              // leading dimension of its transpose buffer
   int smem_lq, smem_svd, smem_rc;
   // debug dump (tnsu_debug_edge)
   double *dbg_sigma;

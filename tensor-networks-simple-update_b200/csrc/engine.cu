@@ -25,6 +25,7 @@ struct LevelCfg {
   int nt = 32;       // threads per side CTA
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
+  int svdw_precond = 0, svdw_ldt = 0;
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
 };
 
@@ -67,6 +68,7 @@ struct tnsu_engine {
   std::vector<int> post_dims;
   bool plan_valid = false, plan_steady = false;
   bool force_unrolled_lq = false;         // TNSU_LQ=unrolled: keep the fully unrolled K1 (A/B comparisons)
+  bool svd_precond = true;                // TNSU_SVD_PRECOND=0: plain Jacobi in the warp SVD (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
@@ -236,6 +238,13 @@ static int plan_sweep(tnsu_engine *e) {
         }
       c.svdw_np = std::max(1, (maxnc + 1) / 2);
       c.svdw_group_doubles = 2 * ldm2 + e->d4 + e->dcap + 2 * c.svdw_rows * 2 * c.svdw_np;
+      if (e->svd_precond && maxnr >= 8) {
+        // one column of A' = theta^T (nj x ni) and of Q^T (nj x nj) per lane: the group spans max(ni, nj) lanes
+        c.svdw_precond = 1;
+        c.svdw_np = std::max(1, (maxnr + 1) / 2);
+        c.svdw_ldt = std::max(2 * c.svdw_np, 2 * c.svdw_rows) | 1;
+        c.svdw_group_doubles = 2 * ldm2 + e->d4 + e->dcap + 2 * c.svdw_rows * c.svdw_ldt + 2 * c.svdw_rows + 2;
+      }
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
     if (std::max(c.smem_lq, std::max(c.smem_svd, c.smem_rc)) > SMEM_LIMIT)
@@ -351,6 +360,8 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_np = c.svdw_np;
     p.svdw_rows = c.svdw_rows;
     p.svdw_group_doubles = c.svdw_group_doubles;
+    p.svdw_precond = c.svdw_precond;
+    p.svdw_ldt = c.svdw_ldt;
     p.dbg_info = nullptr;
     if (dbg_point >= 0) {
       p.dbg_sigma = e->dbg_sigma;
@@ -672,6 +683,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   {
     const char *env = getenv("TNSU_SVD");
     e->force_smem_svd = env && std::string(env) == "smem";
+    env = getenv("TNSU_SVD_PRECOND");
+    if (env && std::string(env) == "0") e->svd_precond = false;
     env = getenv("TNSU_LQ");
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
   }
