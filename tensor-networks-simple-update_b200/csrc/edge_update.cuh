@@ -399,9 +399,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     rowin[r] = (r < M) ? (int)(s * sd.in_stride_phys + x * sd.in_stride[sd.bond_leg]) : 0;
   }
   for (int idx = lt; idx < ldm * ldm; idx += nt) matL[idx] = 0.0;
-  __syncthreads();
 
-  // ---- load my columns, absorbing the environment weights ----
+  // ---- load my columns (raw: the loads are in flight while the weights arrive in shared memory) ----
   const double *tbase = (const double *)sd.base + (size_t)b * sd.point_stride;
   const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
   double col[NCOLS][MMAX];
@@ -410,14 +409,32 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   for (int j = 0; j < NCOLS; ++j) {
     const int c = lt + j * nt;
     cvalid[j] = c < N;
-    const ColInfo ci = decode_column(sd, cvalid[j] ? c : 0, wleg, p.dcap);
-    const double wc = ci.w * tsc;
+    // element offset of (s = 0, x_k = 0) of column c: mixed-radix decode over the other legs
+    long long off = 0;
+    int rem = cvalid[j] ? c : 0;
+    for (int l = sd.nlegs - 1; l >= 0; --l) {
+      if (l == sd.bond_leg) continue;
+      const int dim = sd.dims[l];
+      const int x = rem % dim;
+      rem /= dim;
+      off += (long long)x * sd.in_stride[l];
+    }
+    const int bstride = (int)sd.in_stride[sd.bond_leg];
+    const long long pstride = sd.in_stride_phys;
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) {
-      double v = 0.0;
-      if (cvalid[j] && r < M) v = tbase[ci.in_off + rowin[r]] * wc;
-      col[j][r] = v;
+      const int sph = r / Dk, x = r - sph * Dk;  // Dk is CTA uniform
+      col[j][r] = (cvalid[j] && r < M) ? tbase[off + sph * pstride + (long long)x * bstride] : 0.0;
     }
+  }
+  __syncthreads();
+  // ---- absorb the environment weights and the lazy normalisation ----
+#pragma unroll
+  for (int j = 0; j < NCOLS; ++j) {
+    const ColInfo ci = decode_column(sd, cvalid[j] ? lt + j * nt : 0, wleg, p.dcap);
+    const double wc = ci.w * tsc;
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) col[j][r] *= wc;
   }
   double *ybase = (double *)sd.ybase + (size_t)b * sd.point_stride;
 
@@ -463,8 +480,19 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
         }
         if (lane < MMAX) red[(buf * TNSU_MAX_WARPS + wl) * MMAX + q] = g;
         __syncthreads();
-        g = 0.0;
-        for (int w = 0; w < nwarps; ++w) g += red[(buf * TNSU_MAX_WARPS + w) * MMAX + q];
+        {
+          const double *rr = red + (size_t)buf * TNSU_MAX_WARPS * MMAX + q;
+          double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+          int w = 0;
+          for (; w + 4 <= nwarps; w += 4) {
+            g0 += rr[w * MMAX];
+            g1 += rr[(w + 1) * MMAX];
+            g2 += rr[(w + 2) * MMAX];
+            g3 += rr[(w + 3) * MMAX];
+          }
+          for (; w < nwarps; ++w) g0 += rr[w * MMAX];
+          g = (g0 + g1) + (g2 + g3);
+        }
         const double mycol = colk[buf * MMAX + q];
         const double alpha = colk[buf * MMAX + u];
         const double gk = __shfl_sync(0xffffffffu, g, u);
@@ -538,9 +566,16 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     static_for<0, MMAX>([&](auto kk_c) {
       constexpr int kk = decltype(kk_c)::value;
       if (kk < K) {
-        double a = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four partial sums: the chain is latency bound
 #pragma unroll
-        for (int j = 0; j < kk; ++j) a = fma(trow[j], matZ[j * ldm + kk], a);
+        for (int j = 0; j < kk; ++j) {
+          const double z = matZ[j * ldm + kk];
+          if ((j & 3) == 0) a0 = fma(trow[j], z, a0);
+          if ((j & 3) == 1) a1 = fma(trow[j], z, a1);
+          if ((j & 3) == 2) a2 = fma(trow[j], z, a2);
+          if ((j & 3) == 3) a3 = fma(trow[j], z, a3);
+        }
+        const double a = (a0 + a1) + (a2 + a3);
         const double tk = tau_s[kk];
         trow[kk] = (lane < kk) ? -(a * tk) : (lane == kk ? tk : 0.0);
       }
