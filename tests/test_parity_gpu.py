@@ -119,6 +119,52 @@ def test_reference_end_to_end_energies(tnsu, capsys):
     capsys.readouterr()
 
 
+@pytest.mark.parametrize("lattice,d_max,j,h,field,expected,tol", [
+    ("chain", 10, 1.0, 0.0, None, -0.44304, 2e-4),      # tests/test_main.py:38-40 (bond growth 2 -> 4 -> 8 -> 10, M > N)
+    ("cube", 2, 1.0, 0.0, None, -0.89253, 3e-2),         # tests/test_main.py:48-50 (z = 6)
+    ("pyrochlore", 3, -1.0, 0.1, "z", -0.80000, 2e-3),   # tests/test_main.py:53-57 (ferromagnet in a field)
+])
+def test_reference_experiments(tnsu, capsys, lattice, d_max, j, h, field, expected, tol):
+    """The reference's remaining end-to-end tests, re-stated on the drop-in API with the reference's own recipe
+    (examples.py:200-310, :440-535: seed 42, virtual_dim 2, default dt schedule, 200 iterations per dt, tol 1e-6)
+    and the reference's tolerances."""
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    smat = tnsu.smc.infinite_structure_matrix_dict(lattice)
+    np.random.seed(42)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=2, spin_dim=2)
+    s_k = [] if field is None else [{"x": sx, "y": sy, "z": sz}[field]]
+    su = tnsu.SimpleUpdate(tn, [j] * smat.shape[1], h, [sx, sy, sz], [sx, sy, sz], s_k,
+                           [0.1, 0.01, 0.001, 0.0001, 0.00001], d_max=d_max, max_iterations=200, convergence_error=1e-6,
+                           log_energy=True, print_process=False)
+    su.run()
+    capsys.readouterr()
+    assert abs(su.energy_per_site() - expected) < tol
+    assert all(len(w) <= d_max for w in tn.weights)
+
+
+def test_svd_kernels_agree(tnsu, monkeypatch):
+    """The register-resident warp SVD (with and without the pivoted-QR preconditioner) and the shared-memory
+    Jacobi kernel are interchangeable: same weights and energy on the BASELINE config-2 shape."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    results = []
+    for env in ({}, {"TNSU_SVD_PRECOND": "0"}, {"TNSU_SVD": "smem"}, {"TNSU_LQ": "unrolled"}):
+        for k in ("TNSU_SVD_PRECOND", "TNSU_SVD", "TNSU_LQ"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        np.random.seed(5)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+        su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1], d_max=8, print_process=False)
+        su.dt = 0.1
+        for _ in range(3):
+            su.simple_update()
+        results.append(([w.copy() for w in tn.weights], su.energy_per_site()))
+    for w, e in results[1:]:
+        assert max(np.abs(a - b).max() for a, b in zip(w, results[0][0])) < 1e-12
+        assert abs(e - results[0][1]) < 1e-12
+
+
 def test_batch_matches_single_and_oracle(tnsu):
     """A batch of TFI points with different fields: every point equals its own single-network run and the
     oracle, i.e. batching does not couple points."""
