@@ -66,6 +66,9 @@ struct EdgeLaunch {
   int nr_max;                // largest theta row count (after the rows >= cols transposition) in this launch
   int nt;                    // threads per side CTA (multiple of 32)
   int lq_rolled;             // real float64: lq_rolled_kernel instead of lq_kernel
+  int lq_stream_grid;        // > 0: persistent streaming variant (TMA-staged tensors) with this many CTAs
+  int lq_stage_off;          // byte offset of the staging buffer in dynamic shared memory
+  int lq_stage_doubles;      // its size
   int svdw_np;               // register-resident warp SVD (svd_warp.cuh): processors (column pairs) per theta, 0 = not used
   int svdw_rows;             // rows of [A] per lane = template R of svd_warp_kernel
   int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
@@ -354,30 +357,66 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
 #define LQR_U 4       // steps per rotation block
 #define LQR_TPLD 33   // leading dimension of the per-warp transpose buffer
 
-template <int MMAX, int NCOLS>
+// mbarrier / bulk-copy (TMA) helpers for the streaming variant
+DEV unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+DEV void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void bulk_g2s(void *dst_smem, const void *src_global, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// STREAM = true: persistent CTAs (grid = resident CTAs) loop over the (item, side) work list; the site tensor of the
+// NEXT work item is copied global -> shared by one TMA bulk copy (cp.async.bulk + mbarrier) while the Householder
+// steps of the current one run, so the 64 KiB load latency that opened every CTA of the one-shot kernel
+// (19 % of its stall samples, profiles/r01e) is off the critical path.
+// optional per-phase cycle counters of the Householder step (compile with -DLQR_PROFILE; read through tnsu_debug_edge,
+// info[11..15] = dots+transpose-store | warp sum | barrier | cross-warp sum+scalar | update+store, summed over the steps)
+#ifdef LQR_PROFILE
+#define LQR_CLK(name) const long long name = clock64()
+#define LQR_ACC() do { prof[0] += c1 - c0; prof[1] += c2 - c1; prof[2] += c3 - c2; prof[3] += c4 - c3; prof[4] += c5 - c4; } while (0)
+#define LQR_DUMP() do { if (p.dbg_info != nullptr && b == p.dbg_point && side == 0 && lt == 0) for (int i_ = 0; i_ < 5; ++i_) p.dbg_info[11 + i_] = (int)prof[i_]; } while (0)
+#else
+#define LQR_CLK(name)
+#define LQR_ACC()
+#define LQR_DUMP()
+#endif
+
+template <int MMAX, int NCOLS, bool STREAM>
 __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq_rolled_kernel(const EdgeLaunch<double> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int item = blockIdx.x >> 1;
-  const int side = blockIdx.x & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
-  if (p.active != nullptr && p.active[b] == 0) return;
-
-  const EdgeDesc &ed = p.descs[ek];
-  const SideDesc &sd = ed.s[side];
   const int nt = blockDim.x;
   const int lt = threadIdx.x;
   const int lane = lt & 31;
   const int wl = lt >> 5;
   const int nwarps = nt >> 5;
-  const int M = sd.M, N = sd.N, K = sd.K;
-  const int Dk = ed.Dk;
   const int ldm = p.ldm;
   constexpr int PARTS = 32 / MMAX;  // lanes sharing one register row in the transpose reduction
   const int q = lane & (MMAX - 1);  // the register row this lane finalises
   const int part = lane / MMAX;
+  (void)PARTS;
 
-  // shared memory: wleg | rowin | red | colk | matL | matZ | matT | matY | tau | tp[nwarps]
+  // shared memory: wleg | rowin | red | colk | matL | matZ | matT | matY | tau | tp[nwarps] | (stream: stage | mbarrier)
   double *wleg = (double *)smem_raw;                                  // [MAX_LEGS][dcap]
   int *rowin = (int *)(wleg + TNSU_MAX_LEGS * p.dcap);                // [MMAX]
   double *red = (double *)(rowin + MMAX + (MMAX & 1));                // [2][TNSU_MAX_WARPS][MMAX]
@@ -388,6 +427,50 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   double *matY = matT + ldm * ldm;                                    // first K columns of Y^H
   double *tau_s = matY + ldm * ldm;                                   // [MMAX]
   double *tp = tau_s + MMAX + (size_t)wl * MMAX * LQR_TPLD;           // [MMAX][LQR_TPLD] per warp
+  double *stage = (double *)(smem_raw + p.lq_stage_off);              // staged site tensor (STREAM)
+  unsigned long long *bar = (unsigned long long *)(stage + p.lq_stage_doubles);
+
+  const int n_work = 2 * p.batch * p.n_level_edges;
+  unsigned parity = 0;
+  // issue the bulk copy of work item w2's tensor (thread 0 only); returns false when that item is skipped
+  auto issue = [&](int w2) {
+    const int item2 = w2 >> 1, side2 = w2 & 1;
+    const int b2 = item2 / p.n_level_edges;
+    if (p.active != nullptr && p.active[b2] == 0) return;
+    const EdgeDesc &ed2 = p.descs[p.level_edges[item2 - b2 * p.n_level_edges]];
+    const SideDesc &sd2 = ed2.s[side2];
+    const unsigned bytes = (unsigned)((sd2.in_stride_phys * ed2.d * 8 + 15) & ~15LL);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(stage, (const double *)sd2.base + (size_t)b2 * sd2.point_stride, bytes, bar);
+  };
+  if constexpr (STREAM) {
+    if (lt == 0) {
+      mbar_init(bar, 1);
+      fence_proxy_async();
+    }
+    __syncthreads();
+    if (lt == 0 && (int)blockIdx.x < n_work) issue(blockIdx.x);
+  }
+
+  for (int w = blockIdx.x; w < n_work; w += (STREAM ? (int)gridDim.x : n_work)) {
+  const int item = w >> 1;
+  const int side = w & 1;
+  const int b = item / p.n_level_edges;
+  const int ek = p.level_edges[item - b * p.n_level_edges];
+  if (p.active != nullptr && p.active[b] == 0) {
+    if constexpr (STREAM) {
+      // nothing was staged for this item; stage the next one now (the buffer is free)
+      if (lt == 0 && w + (int)gridDim.x < n_work) issue(w + gridDim.x);
+      continue;
+    } else {
+      return;
+    }
+  }
+
+  const EdgeDesc &ed = p.descs[ek];
+  const SideDesc &sd = ed.s[side];
+  const int M = sd.M, N = sd.N, K = sd.K;
+  const int Dk = ed.Dk;
 
   const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
   for (int idx = lt; idx < sd.nlegs * p.dcap; idx += nt) {
@@ -401,7 +484,11 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   for (int idx = lt; idx < ldm * ldm; idx += nt) matL[idx] = 0.0;
 
   // ---- load my columns (raw: the loads are in flight while the weights arrive in shared memory) ----
-  const double *tbase = (const double *)sd.base + (size_t)b * sd.point_stride;
+  if constexpr (STREAM) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
+  const double *tbase = STREAM ? (const double *)stage : (const double *)sd.base + (size_t)b * sd.point_stride;
   const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
   double col[NCOLS][MMAX];
   bool cvalid[NCOLS];
@@ -428,6 +515,13 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     }
   }
   __syncthreads();
+  if constexpr (STREAM) {
+    // every thread has copied its columns out of the staging buffer: refill it for this CTA's next work item
+    if (lt == 0 && w + (int)gridDim.x < n_work) {
+      fence_proxy_async();
+      issue(w + gridDim.x);
+    }
+  }
   // ---- absorb the environment weights and the lazy normalisation ----
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
@@ -439,6 +533,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   double *ybase = (double *)sd.ybase + (size_t)b * sd.point_stride;
 
   // ---- Householder steps, LQR_U per rotation block ----
+  long long prof[5] = {0, 0, 0, 0, 0};
+  (void)prof;
 #pragma unroll 1
   for (int kk0 = 0; kk0 < K; kk0 += LQR_U) {
     static_for<0, LQR_U>([&](auto u_c) {
@@ -446,6 +542,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
       const int kk = kk0 + u;
       if (kk < K) {
         const int buf = kk & 1;
+        LQR_CLK(c0);
         if (lt == kk) {  // column kk is column j = 0 of thread kk (kk < 32 <= nt)
 #pragma unroll
           for (int i = 0; i < MMAX; ++i) colk[buf * MMAX + i] = col[0][i];
@@ -462,6 +559,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
           tp[i * LQR_TPLD + lane] = a;
         }
         __syncwarp();
+        LQR_CLK(c1);
         // lane (q, part) sums MMAX of the 32 lane partials of register row q, then the parts combine
         double g;
         {
@@ -478,8 +576,10 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
 #pragma unroll
           for (int m = MMAX; m < 32; m *= 2) g += __shfl_xor_sync(0xffffffffu, g, m);
         }
+        LQR_CLK(c2);
         if (lane < MMAX) red[(buf * TNSU_MAX_WARPS + wl) * MMAX + q] = g;
         __syncthreads();
+        LQR_CLK(c3);
         {
           const double *rr = red + (size_t)buf * TNSU_MAX_WARPS * MMAX + q;
           double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
@@ -526,6 +626,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
           }
         }
         if (!is_row) w_l = 0.0;
+        LQR_CLK(c4);
         // rank-1 update of the matrix rows still to be reduced (other register rows get w = 0)
 #pragma unroll
         for (int i = u + 1; i < MMAX; ++i) {
@@ -542,6 +643,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
           if (cvalid[j]) ybase[(size_t)kk * N + c] = y;
           if (j == 0 && lt < K) matY[kk * ldm + lt] = y;
         }
+        LQR_CLK(c5);
+        LQR_ACC();
       }
     });
     // rotate the register rows by LQR_U: the block's reflectors move behind the matrix rows
@@ -557,6 +660,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     }
   }
   __syncthreads();
+  LQR_DUMP();
 
   // compact-WY factor: T[:k,k] = -tau_k T[:k,:k] Z[:k,k], T[k,k] = tau_k   (lane r holds row r)
   if (wl == 0) {
@@ -601,6 +705,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     const int r = idx / K, qq = idx - r * K;
     gL[r * ldm + qq] = matL[r * ldm + qq];
   }
+  if constexpr (STREAM) __syncthreads();  // the shared matrices are reused by the next work item
+  }  // work loop
 }
 
 // =============================================================================================
@@ -1009,7 +1115,19 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
 // ---------------------------------------------------------------------------------------------
 template <int MM, int NC>
 cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
-  auto kern = lq_rolled_kernel<MM, NC>;
+  if (p.lq_stream_grid > 0) {
+    auto kern = lq_rolled_kernel<MM, NC, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+      if (s != cudaSuccess) return s;
+      attr_done = true;
+    }
+    const int grid = (2 * n_items < p.lq_stream_grid) ? 2 * n_items : p.lq_stream_grid;
+    kern<<<grid, p.nt, p.smem_lq, st>>>(p);
+    return cudaGetLastError();
+  }
+  auto kern = lq_rolled_kernel<MM, NC, false>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);

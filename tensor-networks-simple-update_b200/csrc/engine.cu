@@ -26,6 +26,7 @@ struct LevelCfg {
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
   int svdw_precond = 0, svdw_ldt = 0;
+  int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
 };
 
@@ -67,8 +68,11 @@ struct tnsu_engine {
   std::vector<EdgeDesc> h_descs;
   std::vector<int> post_dims;
   bool plan_valid = false, plan_steady = false;
+  bool lq_stream = false;                 // TNSU_LQ_STREAM=1: persistent TMA-staged K1 instead of one-shot CTAs (measured 4 % slower)
+  int num_sms = 148;
   bool force_unrolled_lq = false;         // TNSU_LQ=unrolled: keep the fully unrolled K1 (A/B comparisons)
   bool svd_precond = true;                // TNSU_SVD_PRECOND=0: plain Jacobi in the warp SVD (A/B comparisons)
+  int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
@@ -205,6 +209,8 @@ static int plan_sweep(tnsu_engine *e) {
     bool ok = false;
     const int order2[2] = {2, 1}, order1[2] = {1, 2};
     const int *ncs = (maxN > 128) ? order2 : order1;  // two columns per thread once the matrix is wide
+    if (e->force_ncols == 1) ncs = order1;
+    if (e->force_ncols == 2) ncs = order2;
     for (int o = 0; o < 2 && !ok; ++o) {
       const int nc = ncs[o];
       if (cx && c.mm_t == 32 && nc == 2) continue;  // not instantiated: 256 data registers per thread
@@ -225,6 +231,21 @@ static int plan_sweep(tnsu_engine *e) {
     c.smem_lq = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + (2 * TNSU_MAX_WARPS * c.mm_t + 2 * c.mm_t + 4 * ldm2) * ssz +
                 c.mm_t * 8 + 64;
     if (!cx) c.smem_lq += (c.nt / 32) * c.mm_t * 33 * 8;  // per-warp transpose buffers of lq_rolled_kernel
+    if (!cx && e->lq_stream) {
+      // streaming K1: one staging buffer for the largest site tensor of the level; two CTAs must fit one SM
+      long long stage = 0;
+      for (int ek : e->level_edges[lv])
+        for (int s2 = 0; s2 < 2; ++s2) stage = std::max(stage, e->h_descs[ek].s[s2].in_stride_phys * (long long)e->d);
+      stage = (stage + 1) & ~1LL;
+      const int off = (c.smem_lq + 15) & ~15;
+      const long long total = off + stage * 8 + 16;
+      if (2 * (total + 1024) <= SMEM_LIMIT) {
+        c.lq_stage_off = off;
+        c.lq_stage_doubles = (int)stage;
+        c.smem_lq = (int)total;
+        c.lq_stream_grid = 2 * e->num_sms;
+      }
+    }
     c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + c.ldv * c.ldv) * ssz + 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
     c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
     // real thetas of at most 32 x 32 take the register-resident warp kernel (svd_warp.cuh)
@@ -357,6 +378,9 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.smem_svd = c.smem_svd;
     p.smem_rc = c.smem_rc;
     p.lq_rolled = (!e->force_unrolled_lq && e->dtype == TNSU_F64) ? 1 : 0;
+    p.lq_stream_grid = c.lq_stream_grid;
+    p.lq_stage_off = c.lq_stage_off;
+    p.lq_stage_doubles = c.lq_stage_doubles;
     p.svdw_np = c.svdw_np;
     p.svdw_rows = c.svdw_rows;
     p.svdw_group_doubles = c.svdw_group_doubles;
@@ -685,6 +709,10 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_smem_svd = env && std::string(env) == "smem";
     env = getenv("TNSU_SVD_PRECOND");
     if (env && std::string(env) == "0") e->svd_precond = false;
+    env = getenv("TNSU_LQ_STREAM");
+    e->lq_stream = env && std::string(env) == "1";
+    env = getenv("TNSU_NCOLS");
+    if (env) e->force_ncols = atoi(env);
     env = getenv("TNSU_LQ");
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
   }
@@ -767,6 +795,7 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   } while (0)
 
   CKC(cudaSetDevice(device));
+  CKC(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (stream) {
     e->stream = (cudaStream_t)stream;
   } else {

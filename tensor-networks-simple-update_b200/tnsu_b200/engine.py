@@ -208,7 +208,8 @@ class Engine:
         mi, ki, mj, kj, ni, nj, dnew, sweeps = (int(x) for x in info[:8])
         return dict(l_i=li[: mi * ki].reshape(mi, ki), l_j=lj[: mj * kj].reshape(mj, kj), sigma=sig[: min(ni, nj)],
                     d_new=dnew, svd_sweeps=sweeps,
-                    phase_cycles=dict(zip(["theta", "jacobi", "extract"], (int(x) for x in info[8:11]))))
+                    phase_cycles=dict(zip(["theta", "jacobi", "extract"], (int(x) for x in info[8:11]))),
+                    lq_cycles=[int(x) for x in info[11:16]])
 
 
 def schedule_levels(structure_matrix) -> np.ndarray:
