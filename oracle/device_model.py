@@ -6,7 +6,8 @@ gauge-equivalent route ("Kernel math"):
   * in-place Householder LQ on the rows of the absorbed bond matrix P (reflector k is left in row k),
   * compact-WY form of the reflectors, so that P' = r~ . Q becomes one sync-free small GEMM
         P' = [r~ 0] - (r~ . Y1 . T^H) . Y^H,
-  * one-sided (Hestenes) Jacobi SVD of theta with accumulated right vectors.
+  * one-sided (Hestenes) Jacobi SVD of theta with accumulated right vectors; for real thetas up to 32 x 32 in the
+    odd-even ordering after a pivoted-QR preconditioner (`svd_preconditioned`, mirrors csrc/svd_warp.cuh).
 
 This module states that route step by step in numpy with the same index conventions as
 `csrc/edge_update.cuh`, so the math can be checked against the oracle on the CPU
@@ -127,6 +128,75 @@ def jacobi_svd(a, tol=1e-15, max_sweeps=60):
     if transposed:
         return v, sv, np.conj(u.T)
     return u, sv, np.conj(v.T)
+
+
+def qr_column_pivoting(a):
+    """Householder QR with column pivoting in the form `svd_warp_kernel` uses it: the columns never move
+    (the kernel keeps one column per lane), pivots are only CHOSEN by trailing norm, so the result is
+    R~ = R P^T with A = Q R~.  Returns (q_thin, r_tilde), q_thin: rows x steps, r_tilde: steps x cols."""
+    a = np.array(a, dtype=float)
+    rows, cols = a.shape
+    steps = min(rows, cols)
+    z = np.eye(rows)  # accumulates Q^T = H_{steps-1} ... H_0
+    done = np.zeros(cols, dtype=bool)
+    for j in range(steps):
+        norms = np.where(done, -1.0, np.sum(a[j:, :] ** 2, axis=0))
+        piv = int(np.argmax(norms))
+        done[piv] = True
+        w = a[:, piv].copy()
+        w[:j] = 0.0
+        n2 = float(w @ w)
+        if n2 > 0.0:
+            norm = np.sqrt(n2)
+            alpha = w[j]
+            w[j] = alpha + (norm if alpha >= 0 else -norm)
+            tau = 1.0 / (n2 + norm * abs(alpha))
+            a -= np.outer(w, tau * (w @ a))
+            z -= np.outer(w, tau * (w @ z))
+    return z[:steps, :].T, a[:steps, :]
+
+
+def jacobi_odd_even(x, acc, tol=1.5e-15, max_sweeps=60):
+    """One-sided Jacobi on the columns of X with the accumulator `acc` rotated along, in the odd-even
+    transposition ordering of `svd_warp_kernel`: step A pairs positions (2k, 2k+1), step B pairs (2k+1, 2k+2),
+    every rotation writes its outputs swapped, so that all pairs meet once in n steps.  Returns the rotated
+    (x, acc, sweeps)."""
+    x, acc = np.array(x, dtype=float), np.array(acc, dtype=float)
+    n = x.shape[1]
+    for sweep in range(max_sweeps):
+        rotated = False
+        for step in range(n + (n & 1)):
+            for p in range(step % 2, n - 1, 2):
+                q = p + 1
+                al, be, ga = x[:, p] @ x[:, p], x[:, q] @ x[:, q], x[:, p] @ x[:, q]
+                c, s = 1.0, 0.0
+                if ga * ga > tol * tol * al * be and ga != 0.0:
+                    rotated = True
+                    delta = be - al
+                    inv_r = 1.0 / np.sqrt(delta * delta + 4.0 * ga * ga)
+                    c2 = 0.5 + 0.5 * abs(delta) * inv_r
+                    c = np.sqrt(c2)
+                    s = (-ga if delta < 0 else ga) * inv_r / c
+                for m in (x, acc):
+                    pc, qc = m[:, p].copy(), m[:, q].copy()
+                    m[:, p] = s * pc + c * qc
+                    m[:, q] = c * pc - s * qc
+        if not rotated:
+            return x, acc, sweep + 1
+    return x, acc, max_sweeps
+
+
+def svd_preconditioned(theta):
+    """theta = U diag(s) V^T the way `svd_warp_kernel` computes it: A' = theta^T, A' = Q R~ (pivoted QR),
+    Jacobi on X = R~^T with the accumulator started at Q:  X W = Y  =>  A' = (Q W)(Y)^T, so the right vectors of
+    theta are the final accumulator and the left vectors the normalised final X columns."""
+    q_thin, r_tilde = qr_column_pivoting(np.array(theta, dtype=float).T)
+    x, acc, sweeps = jacobi_odd_even(r_tilde.T, q_thin)
+    sv = np.sqrt(np.sum(x * x, axis=0))
+    order = np.argsort(-sv, kind="stable")
+    sv, x, acc = sv[order], x[:, order], acc[:, order]
+    u = x / np.where(sv > 0, sv, 1.0)
+    return u, sv, acc.T, sweeps
 
 
 def edge_update(tensors, weights, smat, ek, gate, d_max):
