@@ -43,11 +43,10 @@ class TensorNetwork:
         real_init = random_init_real_loc is not None and random_init_real_scale is not None
         imag_init = random_init_imag_loc is not None and random_init_imag_scale is not None
         assert real_init or imag_init, (
-            "'real' or 'imag' loc and scale values for tensors' random initialization must be float values, "
-            f"instead got: {random_init_real_loc=}, {random_init_real_scale=}, {random_init_imag_loc=}, "
-            f"{random_init_imag_scale=}.")
-        assert 0 < spin_dim == int(spin_dim), f"Spin dimension should be an integer larger than 0. Instead got {spin_dim}."
-        assert is_valid(structure_matrix), "Got an invalid structure matrix."
+            "random initialisation needs (loc, scale) for the real part, the imaginary part, or both; got "
+            f"real=({random_init_real_loc}, {random_init_real_scale}) imag=({random_init_imag_loc}, {random_init_imag_scale})")
+        assert 0 < spin_dim == int(spin_dim), f"spin_dim must be a positive integer, got {spin_dim}"
+        assert is_valid(structure_matrix), "invalid structure matrix"
 
         n, m = structure_matrix.shape
         if tensors is None:
@@ -79,31 +78,29 @@ class TensorNetwork:
         self.network_name = network_name
         self.su_logger = None
         self.state_dict = None
-        assert self.is_valid(), "Invalid Tensor Network."
+        assert self.is_valid(), "tensors, weights and structure matrix do not fit together"
 
     # ---- validation (reference :130-175) ----
     def is_valid(self) -> bool:
         n, m = self.structure_matrix.shape
         if m != len(self.weights):
-            print(f"Num of columns in structure_matrix is {m}, while num of weights is {len(self.weights)}. "
-                  "They should be equal !")
+            print(f"structure matrix has {m} columns (edges) but {len(self.weights)} weight vectors were given")
             return False
         if n != len(self.tensors):
-            print(f"Num of rows in structure_matrix is {n}, while num of tensors is {len(self.tensors)}. "
-                  "They should be equal, a row for each tensor.")
+            print(f"structure matrix has {n} rows (tensors) but {len(self.tensors)} tensors were given")
             return False
         for i in range(n):
             legs = int(np.sum(self.structure_matrix[i, :] > 0))
             if self.tensors[i].ndim - 1 != legs:
-                print(f"tensor [{i}] is connected to {self.tensors[i].ndim - 1}  weight vectors but have {legs} "
-                      "virtual dimensions.")
+                print(f"tensor {i}: {self.tensors[i].ndim - 1} virtual axes, but row {i} of the structure matrix "
+                      f"connects it to {legs} edges")
                 return False
         for i in range(n):
             for j in np.nonzero(self.structure_matrix[i, :])[0]:
                 axis = self.structure_matrix[i, j]
                 if self.tensors[i].shape[axis] != len(self.weights[j]):
-                    print(f"Dimension {axis} size of Tensor [{i}] is {self.tensors[i].shape[axis]}, while size of "
-                          f"weight vector [{j}] is {len(self.weights[j])}. They should be equal !")
+                    print(f"tensor {i} axis {axis} has size {self.tensors[i].shape[axis]} but the weight vector of "
+                          f"edge {j} has {len(self.weights[j])} entries")
                     return False
         return True
 
@@ -122,7 +119,7 @@ class TensorNetwork:
         self.network_name, self.su_logger = sd["network_name"], sd["su_logger"]
 
     def save_network(self, filename="tensor_network"):
-        print("Saving a Tensor Network...")
+        print(f"saving tensor network {self.network_name or filename!r}")
         self.create_state_dict()
         if self.network_name is None:
             self.network_name = filename
@@ -131,15 +128,14 @@ class TensorNetwork:
             pickle.dump(self.state_dict, outfile, pickle.DEFAULT_PROTOCOL)
 
     def load_network(self, network_full_path=None):
-        print("Loading a Tensor Network...")
+        print("loading tensor network")
         path = os.path.join(self.dir_path, self.network_name + ".pkl") if network_full_path is None else network_full_path
         try:
             with open(path, "rb") as infile:
                 self.state_dict = pickle.load(infile)
                 self.unpack_state_dict()
         except Exception as error:  # noqa: BLE001 - the reference swallows and prints (:226-230)
-            print(f"There was an error in loading the tensor network from path:\n {path}\n"
-                  f"with the next exception:\n {error}.")
+            print(f"could not load a tensor network from {path}: {error!r}")
 
     # ---- structure lookups and host-side weight helpers (reference :232-356) ----
     def get_edges(self, tensor_idx: int) -> dict:
