@@ -25,6 +25,7 @@
 // Gauge: any orthonormal row basis Q is admissible (SURVEY.md §8a "Gauge facts"); weights, RDMs and
 // energies are gauge invariant and are what the parity tests compare.
 #pragma once
+#include <cooperative_groups.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -66,6 +67,9 @@ struct EdgeLaunch {
   int nr_max;                // largest theta row count (after the rows >= cols transposition) in this launch
   int nt;                    // threads per side CTA (multiple of 32)
   int lq_rolled;             // real float64: lq_rolled_kernel instead of lq_kernel
+  int cluster;               // CTAs per (item, side) in K1 (thread-block cluster) and K3 (column slices); 1 = one CTA
+  double *tnorm2;            // [batch][n_tensors] partial ||T'||^2 of the K3 column slices (cluster > 1)
+  unsigned *tticket;         // [batch][n_tensors] arrival counter of the K3 column slices
   int lq_stream_grid;        // > 0: persistent streaming variant (TMA-staged tensors) with this many CTAs
   int lq_stage_off;          // byte offset of the staging buffer in dynamic shared memory
   int lq_stage_doubles;      // its size
@@ -430,6 +434,11 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   double *stage = (double *)(smem_raw + p.lq_stage_off);              // staged site tensor (STREAM)
   unsigned long long *bar = (unsigned long long *)(stage + p.lq_stage_doubles);
 
+  // thread-block cluster (large bond matrices): CL CTAs share one (item, side); CTA `rank` owns columns
+  // [rank*ncl, rank*ncl + ncl) and the per-step Gram row is summed across the cluster through distributed shared memory
+  const int CL = STREAM ? 1 : p.cluster;
+  const int rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
+  double *cpart = (double *)(smem_raw + p.lq_stage_off);              // [2][MMAX] this CTA's partial Gram row (CL > 1)
   const int n_work = 2 * p.batch * p.n_level_edges;
   unsigned parity = 0;
   // issue the bulk copy of work item w2's tensor (thread 0 only); returns false when that item is skipped
@@ -452,7 +461,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     if (lt == 0 && (int)blockIdx.x < n_work) issue(blockIdx.x);
   }
 
-  for (int w = blockIdx.x; w < n_work; w += (STREAM ? (int)gridDim.x : n_work)) {
+  for (int w = (int)(blockIdx.x / CL); w < n_work; w += (STREAM ? (int)gridDim.x : n_work)) {
   const int item = w >> 1;
   const int side = w & 1;
   const int b = item / p.n_level_edges;
@@ -471,6 +480,9 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   const SideDesc &sd = ed.s[side];
   const int M = sd.M, N = sd.N, K = sd.K;
   const int Dk = ed.Dk;
+  const int ncl = (N + CL - 1) / CL;           // columns per CTA of the cluster
+  const int c0 = rank * ncl;                   // my first column
+  const int c_end = min(N, c0 + ncl);
 
   const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
   for (int idx = lt; idx < sd.nlegs * p.dcap; idx += nt) {
@@ -494,8 +506,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   bool cvalid[NCOLS];
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const int c = lt + j * nt;
-    cvalid[j] = c < N;
+    const int c = c0 + lt + j * nt;
+    cvalid[j] = c < c_end;
     // element offset of (s = 0, x_k = 0) of column c: mixed-radix decode over the other legs
     long long off = 0;
     int rem = cvalid[j] ? c : 0;
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   // ---- absorb the environment weights and the lazy normalisation ----
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const ColInfo ci = decode_column(sd, cvalid[j] ? lt + j * nt : 0, wleg, p.dcap);
+    const ColInfo ci = decode_column(sd, cvalid[j] ? c0 + lt + j * nt : 0, wleg, p.dcap);
     const double wc = ci.w * tsc;
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) col[j][r] *= wc;
@@ -543,14 +555,14 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
       if (kk < K) {
         const int buf = kk & 1;
         LQR_CLK(c0);
-        if (lt == kk) {  // column kk is column j = 0 of thread kk (kk < 32 <= nt)
+        if (rank == 0 && lt == kk) {  // column kk is column j = 0 of thread kk of the first CTA (kk < 32 <= nt)
 #pragma unroll
           for (int i = 0; i < MMAX; ++i) colk[buf * MMAX + i] = col[0][i];
         }
         // partial Gram row of the pivot (register row u) with every register row, over my columns c > kk
         double pk[NCOLS];
 #pragma unroll
-        for (int j = 0; j < NCOLS; ++j) pk[j] = (j > 0 || lt > kk) ? col[j][u] : 0.0;
+        for (int j = 0; j < NCOLS; ++j) pk[j] = (rank > 0 || j > 0 || lt > kk) ? col[j][u] : 0.0;
 #pragma unroll
         for (int i = 0; i < MMAX; ++i) {
           double a = col[0][i] * pk[0];
@@ -593,8 +605,20 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
           for (; w < nwarps; ++w) g0 += rr[w * MMAX];
           g = (g0 + g1) + (g2 + g3);
         }
-        const double mycol = colk[buf * MMAX + q];
-        const double alpha = colk[buf * MMAX + u];
+        const double *colk_src = colk;
+        if (CL > 1) {
+          // sum the CTA partials across the cluster; column kk lives in the first CTA
+          namespace cg = cooperative_groups;
+          cg::cluster_group cluster = cg::this_cluster();
+          if (wl == 0 && lane < MMAX) cpart[buf * MMAX + q] = g;
+          cluster.sync();
+          double tot = 0.0;
+          for (int r = 0; r < CL; ++r) tot += cluster.map_shared_rank(cpart, r)[buf * MMAX + q];
+          g = tot;
+          colk_src = cluster.map_shared_rank(colk, 0);
+        }
+        const double mycol = colk_src[buf * MMAX + q];
+        const double alpha = colk_src[buf * MMAX + u];
         const double gk = __shfl_sync(0xffffffffu, g, u);
         const double norm2 = fma(alpha, alpha, gk);
         // roles of register row q: q < u reflector kk0+q; q == u pivot; u < q < MMAX-kk0 matrix row kk0+q;
@@ -637,11 +661,11 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
         // the pivot row becomes the stored reflector: row kk of Y^H goes to global (coalesced) and to matY
 #pragma unroll
         for (int j = 0; j < NCOLS; ++j) {
-          const int c = lt + j * nt;
+          const int c = c0 + lt + j * nt;
           const double y = (c == kk) ? head : (c < kk ? 0.0 : col[j][u]);
           col[j][u] = y;
           if (cvalid[j]) ybase[(size_t)kk * N + c] = y;
-          if (j == 0 && lt < K) matY[kk * ldm + lt] = y;
+          if (rank == 0 && j == 0 && lt < K) matY[kk * ldm + lt] = y;
         }
         LQR_CLK(c5);
         LQR_ACC();
@@ -661,6 +685,11 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   }
   __syncthreads();
   LQR_DUMP();
+  if (CL > 1) {
+    // no CTA may leave while a peer can still read its shared memory; only the first CTA writes L and S
+    cooperative_groups::this_cluster().sync();
+    if (rank != 0) return;
+  }
 
   // compact-WY factor: T[:k,k] = -tau_k T[:k,:k] Z[:k,k], T[k,k] = tau_k   (lane r holds row r)
   if (wl == 0) {
@@ -1003,8 +1032,10 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
 template <typename S, int MMAX, int NCOLS>
 __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompose_kernel(const EdgeLaunch<S> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int item = blockIdx.x >> 1;
-  const int side = blockIdx.x & 1;
+  const int CL = p.cluster;  // column slices per (item, side)
+  const int rank = (int)(blockIdx.x % CL);
+  const int item = (int)(blockIdx.x / CL) >> 1;
+  const int side = (int)(blockIdx.x / CL) & 1;
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
@@ -1018,6 +1049,9 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
   const int N = sd.N, K = sd.K, Mout = sd.Mout;
   const int Dnew = ed.Dnew;
   const int ldm = p.ldm;
+  const int ncl = (N + CL - 1) / CL;
+  const int c0 = rank * ncl;
+  const int c_end = min(N, c0 + ncl);
 
   // shared memory: wleg | rowout | matR | matS | matC | nred
   double *wleg = (double *)smem_raw;
@@ -1050,14 +1084,14 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
   double inv_w[NCOLS];
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const int c = lt + j * nt;
+    const int c = c0 + lt + j * nt;
 #pragma unroll
-    for (int k = 0; k < MMAX; ++k) col[j][k] = (c < N && k < K) ? ybase[(size_t)k * N + c] : from_real<S>(0.0);
+    for (int k = 0; k < MMAX; ++k) col[j][k] = (c < c_end && k < K) ? ybase[(size_t)k * N + c] : from_real<S>(0.0);
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const ColInfo ci = decode_column(sd, lt + j * nt, wleg, p.dcap);
+    const ColInfo ci = decode_column(sd, (c0 + lt + j * nt < c_end) ? c0 + lt + j * nt : 0, wleg, p.dcap);
     out_off[j] = ci.out_off;
     inv_w[j] = ci.inv_w;
   }
@@ -1077,7 +1111,7 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
     S o[NCOLS];
 #pragma unroll
     for (int j = 0; j < NCOLS; ++j) {
-      const int c = lt + j * nt;
+      const int c = c0 + lt + j * nt;
       o[j] = (c < K) ? matR[i * ldm + c] : from_real<S>(0.0);
     }
 #pragma unroll
@@ -1091,8 +1125,8 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
     const long long ro = rowout[i];
 #pragma unroll
     for (int j = 0; j < NCOLS; ++j) {
-      const int c = lt + j * nt;
-      if (c < N) {
+      const int c = c0 + lt + j * nt;
+      if (c < c_end) {
         const S v = o[j] * inv_w[j];
         n2 += abs2(v);
         tbase[out_off[j] + ro] = v;
@@ -1106,7 +1140,21 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
   if (lt == 0) {
     double tot = 0.0;
     for (int w = 0; w < nwarps; ++w) tot += nred[w];
-    p.tscale[(size_t)b * p.n_tensors + sd.tensor] = 1.0 / sqrt(tot);
+    const size_t ti = (size_t)b * p.n_tensors + sd.tensor;
+    if (CL == 1) {
+      p.tscale[ti] = 1.0 / sqrt(tot);
+    } else {
+      // column slices: the last slice to arrive turns the accumulated norm into the lazy scale
+      atomicAdd(&p.tnorm2[ti], tot);
+      __threadfence();
+      if (atomicAdd(&p.tticket[ti], 1u) == (unsigned)(CL - 1)) {
+        __threadfence();
+        const double all = atomicAdd(&p.tnorm2[ti], 0.0);
+        p.tscale[ti] = 1.0 / sqrt(all);
+        p.tnorm2[ti] = 0.0;
+        p.tticket[ti] = 0u;
+      }
+    }
   }
 }
 
@@ -1133,6 +1181,22 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
     cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
     if (s != cudaSuccess) return s;
     attr_done = true;
+  }
+  if (p.cluster > 1) {
+    // one thread-block cluster per (item, side): the CTAs exchange their partial Gram rows through DSMEM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * n_items * p.cluster);
+    cfg.blockDim = dim3(p.nt);
+    cfg.dynamicSmemBytes = p.smem_lq;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = p.cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
   }
   kern<<<2 * n_items, p.nt, p.smem_lq, st>>>(p);
   return cudaGetLastError();
@@ -1163,7 +1227,7 @@ cudaError_t launch_rc_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t 
     if (s != cudaSuccess) return s;
     attr_done = true;
   }
-  kern<<<2 * n_items, p.nt, p.smem_rc, st>>>(p);
+  kern<<<2 * n_items * p.cluster, p.nt, p.smem_rc, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@ struct LevelCfg {
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
   int svdw_precond = 0, svdw_ldt = 0;
   int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
+  int cluster = 1;                                                   // CTAs per (item, side) in K1 / K3
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
 };
 
@@ -59,6 +60,8 @@ struct tnsu_engine {
   bool profile = false;
   cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
   double *weights = nullptr, *tscale = nullptr, *edge_err = nullptr, *energy = nullptr;
+  double *tnorm2 = nullptr;               // K3 column slices: partial norms and arrival counters per (point, tensor)
+  unsigned *tticket = nullptr;
   void *gates = nullptr, *hams = nullptr, *op_buf = nullptr;
   int n_slots = 0;
   std::vector<char> slot_set;
@@ -221,6 +224,21 @@ static int plan_sweep(tnsu_engine *e) {
       c.nt = nt;
       ok = true;
     }
+    if (!ok && !cx && !e->force_unrolled_lq) {
+      // wide bond matrices: split the columns over a thread-block cluster of 2, 4 or 8 CTAs (K1) / column slices (K3)
+      for (int cl = 2; cl <= 8 && !ok; cl *= 2) {
+        const int ncl = (maxN + cl - 1) / cl;
+        for (int o = 0; o < 2 && !ok; ++o) {
+          const int nc = order2[o];
+          const int nt = ((ncl + nc - 1) / nc + 31) & ~31;
+          if (nt > max_threads(cx, c.mm_t, nc) || nt > TNSU_MAX_WARPS * 32) continue;
+          c.ncols = nc;
+          c.nt = nt;
+          c.cluster = cl;
+          ok = true;
+        }
+      }
+    }
     if (!ok)
       return fail(e, TNSU_E_UNSUPPORTED,
                   "no kernel variant holds a %d x %d bond matrix (%s) in registers; reduce the bond dimension",
@@ -232,7 +250,11 @@ static int plan_sweep(tnsu_engine *e) {
     c.smem_lq = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + (2 * TNSU_MAX_WARPS * c.mm_t + 2 * c.mm_t + 4 * ldm2) * ssz +
                 c.mm_t * 8 + 64;
     if (!cx) c.smem_lq += (c.nt / 32) * c.mm_t * 33 * 8;  // per-warp transpose buffers of lq_rolled_kernel
-    if (!cx && e->lq_stream) {
+    if (c.cluster > 1) {
+      c.lq_stage_off = (c.smem_lq + 15) & ~15;  // the cluster's partial Gram rows [2][MMAX]
+      c.smem_lq = c.lq_stage_off + 2 * c.mm_t * 8 + 16;
+    }
+    if (!cx && e->lq_stream && c.cluster == 1) {
       // streaming K1: one staging buffer for the largest site tensor of the level; two CTAs must fit one SM
       long long stage = 0;
       for (int ek : e->level_edges[lv])
@@ -379,6 +401,9 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.smem_svd = c.smem_svd;
     p.smem_rc = c.smem_rc;
     p.lq_rolled = (!e->force_unrolled_lq && e->dtype == TNSU_F64) ? 1 : 0;
+    p.cluster = c.cluster;
+    p.tnorm2 = e->tnorm2;
+    p.tticket = e->tticket;
     p.lq_stream_grid = c.lq_stream_grid;
     p.lq_stage_off = c.lq_stage_off;
     p.lq_stage_doubles = c.lq_stage_doubles;
@@ -639,7 +664,7 @@ int tnsu_destroy(tnsu_engine *e) {
   if (e->small) cudaFree(e->small);
   for (int k = 0; k < 4; ++k)
     if (e->pev[k]) cudaEventDestroy(e->pev[k]);
-  void *ptrs[] = {e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
+  void *ptrs[] = {e->tnorm2, e->tticket, e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
                   e->rdm_buf, e->site_buf, e->d_descs, e->d_level_edges, e->d_all_edges, e->d_site, e->r_slot,
                   e->r_iter, e->r_step, e->r_active, e->r_conv, e->r_nchecks, e->r_log_slot, e->r_log_step,
                   e->r_nactive, e->r_islast, e->r_log_err, e->r_log_energy, e->dbg_sigma,
@@ -818,6 +843,10 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   CKC(cudaMalloc(&e->weights, B * m * e->dcap * 8));
   CKC(cudaMemsetAsync(e->weights, 0, B * m * e->dcap * 8, e->stream));
   CKC(cudaMalloc(&e->tscale, B * n * 8));
+  CKC(cudaMalloc(&e->tnorm2, B * n * 8));
+  CKC(cudaMemsetAsync(e->tnorm2, 0, B * n * 8, e->stream));
+  CKC(cudaMalloc(&e->tticket, B * n * 4));
+  CKC(cudaMemsetAsync(e->tticket, 0, B * n * 4, e->stream));
   CKC(cudaMalloc(&e->edge_err, B * m * 8));
   CKC(cudaMemsetAsync(e->edge_err, 0, B * m * 8, e->stream));
   CKC(cudaMalloc(&e->energy, B * 8));

@@ -142,6 +142,34 @@ def test_reference_experiments(tnsu, capsys, lattice, d_max, j, h, field, expect
     assert all(len(w) <= d_max for w in tn.weights)
 
 
+@pytest.mark.parametrize("lattice,dim,d", [("peps", 10, 2), ("peps", 12, 2), ("peps", 16, 2), ("triangle", 5, 2), ("chain", 16, 2), ("star", 12, 2), ("peps", 5, 3)])
+def test_large_shapes_match_oracle(tnsu, lattice, dim, d):
+    """Shapes beyond the BASELINE configs, up to what the kernels keep on chip (d*D = 32 rows; up to 1024 columns in
+    one CTA, up to 8 x 512 in a thread-block cluster): two sweeps against the oracle on the same seeded input."""
+    smat = tnsu.smc.infinite_structure_matrix_dict(lattice)
+    sx, sy, sz = tnsu.spin_operators((d - 1) / 2.0)
+    m = smat.shape[1]
+    np.random.seed(21)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim, spin_dim=d)
+    t0, w0 = [np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights]
+    su = tnsu.SimpleUpdate(tn, [1.0] * m, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=dim, print_process=False)
+    su.dt = 0.05
+    model = orc.Model([1.0] * m, 0.0, [sx, sy, sz], [sx, sy, sz], [])
+    for _ in range(2):
+        su.simple_update()
+        orc.sweep(t0, w0, smat, model, 0.05, dim)
+    assert max(np.abs(a - b).max() for a, b in zip(w0, tn.weights)) < TOL_W
+    e_ref = orc.energy_per_site(t0, w0, smat, model)
+    assert abs(su.energy_per_site() - e_ref) < TOL_E * max(1.0, abs(e_ref))
+
+
+def test_unsupported_shapes_fail_loudly(tnsu):
+    """Beyond the on-chip limits the engine refuses (TNSU_E_UNSUPPORTED) instead of falling back to anything."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("triangle")
+    with pytest.raises(tnsu.EngineError, match="UNSUPPORTED"):
+        tnsu.Engine(smat, 2, [8] * smat.shape[1], 8, False)  # 16 x 32768 bond matrices: more columns than a cluster of 8 CTAs holds
+
+
 def test_svd_kernels_agree(tnsu, monkeypatch):
     """The register-resident warp SVD (with and without the pivoted-QR preconditioner) and the shared-memory
     Jacobi kernel are interchangeable: same weights and energy on the BASELINE config-2 shape."""
