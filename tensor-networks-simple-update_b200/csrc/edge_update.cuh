@@ -406,7 +406,7 @@ DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" :::
 #define LQR_DUMP()
 #endif
 
-template <int MMAX, int NCOLS, bool STREAM>
+template <int MMAX, int NCOLS, bool STREAM, bool CLUSTER>
 __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq_rolled_kernel(const EdgeLaunch<double> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nt = blockDim.x;
@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
 
   // thread-block cluster (large bond matrices): CL CTAs share one (item, side); CTA `rank` owns columns
   // [rank*ncl, rank*ncl + ncl) and the per-step Gram row is summed across the cluster through distributed shared memory
-  const int CL = STREAM ? 1 : p.cluster;
-  const int rank = (CL > 1) ? (int)(blockIdx.x % CL) : 0;
+  const int CL = CLUSTER ? p.cluster : 1;  // compile-time 1 in the single-CTA variant: all cluster code folds away
+  const int rank = CLUSTER ? (int)(blockIdx.x % CL) : 0;
   double *cpart = (double *)(smem_raw + p.lq_stage_off);              // [2][MMAX] this CTA's partial Gram row (CL > 1)
   const int n_work = 2 * p.batch * p.n_level_edges;
   unsigned parity = 0;
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
           g = (g0 + g1) + (g2 + g3);
         }
         const double *colk_src = colk;
-        if (CL > 1) {
+        if constexpr (CLUSTER) {
           // sum the CTA partials across the cluster; column kk lives in the first CTA
           namespace cg = cooperative_groups;
           cg::cluster_group cluster = cg::this_cluster();
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   }
   __syncthreads();
   LQR_DUMP();
-  if (CL > 1) {
+  if constexpr (CLUSTER) {
     // no CTA may leave while a peer can still read its shared memory; only the first CTA writes L and S
     cooperative_groups::this_cluster().sync();
     if (rank != 0) return;
@@ -1164,7 +1164,7 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
 template <int MM, int NC>
 cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
   if (p.lq_stream_grid > 0) {
-    auto kern = lq_rolled_kernel<MM, NC, true>;
+    auto kern = lq_rolled_kernel<MM, NC, true, false>;
     static bool attr_done = false;
     if (!attr_done) {
       cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
@@ -1175,15 +1175,15 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
     kern<<<grid, p.nt, p.smem_lq, st>>>(p);
     return cudaGetLastError();
   }
-  auto kern = lq_rolled_kernel<MM, NC, false>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
   if (p.cluster > 1) {
     // one thread-block cluster per (item, side): the CTAs exchange their partial Gram rows through DSMEM
+    auto kernc = lq_rolled_kernel<MM, NC, false, true>;
+    static bool attr_done_c = false;
+    if (!attr_done_c) {
+      cudaError_t s = cudaFuncSetAttribute(kernc, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+      if (s != cudaSuccess) return s;
+      attr_done_c = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * n_items * p.cluster);
     cfg.blockDim = dim3(p.nt);
@@ -1196,7 +1196,14 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
+    return cudaLaunchKernelEx(&cfg, kernc, p);
+  }
+  auto kern = lq_rolled_kernel<MM, NC, false, false>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+    if (s != cudaSuccess) return s;
+    attr_done = true;
   }
   kern<<<2 * n_items, p.nt, p.smem_lq, st>>>(p);
   return cudaGetLastError();
