@@ -74,6 +74,9 @@ class SimpleUpdateBatch:
         self._engine: Engine | None = None
         self._gates_key = None
         self._hams_uploaded = False
+        self._hams_uploaded_obj = None
+        self._synced = None
+        self._synced_engine = None
         self.results = None
 
     # ------------------------------------------------------------------ host-side operators
@@ -102,32 +105,70 @@ class SimpleUpdateBatch:
             field_j += np.kron(np.eye(di), s)
         return self.j_ij[point][ek] * interaction + self.h_k[point] * (field_i / i_neighbors + field_j / j_neighbors)
 
+    def _params_key(self):
+        """Value key of everything the per-edge Hamiltonians depend on (operators by identity)."""
+        return (tuple(id(h) for h in self.hamiltonian),
+                tuple(tuple(complex(x) for x in j) if h is None else () for j, h in zip(self.j_ij, self.hamiltonian)),
+                tuple(complex(h) for h in self.h_k),
+                tuple(id(a) for a in self.s_i), tuple(id(a) for a in self.s_j), tuple(id(a) for a in self.s_k))
+
     def _all_hamiltonians(self):
+        key = self._params_key()
+        if getattr(self, "_hams_cache_key", None) == key:
+            return self._hams_cache
+        out = self._compute_hamiltonians()
+        self._hams_cache_key, self._hams_cache = key, out
+        self._hams_refs = (list(self.hamiltonian), list(self.s_i), list(self.s_j), list(self.s_k))  # keep ids alive
+        return out
+
+    def _compute_hamiltonians(self):
+        """[point][edge] two-site Hamiltonians.  Same arithmetic per element as edge_hamiltonian / the reference
+        (:420-454): j * sum_n kron(s_i[n], s_j[n]) + h * (sum kron(s_k, 1) / z_i + sum kron(1, s_k) / z_j), evaluated
+        for all points of an edge at once."""
         m = self.structure_matrix.shape[1]
-        d2 = self.spin_dims[0] * self.spin_dims[1]
+        di, dj = self.spin_dims
+        d2 = di * dj
         out = np.empty((self.n_points, m, d2, d2), dtype=complex)
-        cache = {}
-        for p in range(self.n_points):
+        interaction = np.zeros((d2, d2), dtype=complex)
+        for a, b in zip(self.s_i, self.s_j):
+            interaction += np.kron(a, b)
+        field_i = np.zeros((d2, d2), dtype=complex)
+        field_j = np.zeros((d2, d2), dtype=complex)
+        for sk in self.s_k:
+            field_i += np.kron(sk, np.eye(dj))
+            field_j += np.kron(np.eye(di), sk)
+        plain = [p for p in range(self.n_points) if self.hamiltonian[p] is None]
+        if plain:
+            h = np.array([self.h_k[p] for p in plain])
             for ek in range(m):
-                shared = self.hamiltonian[p] is not None
-                key = (id(self.hamiltonian[p]),) if shared else (id(self.j_ij[p]), self.j_ij[p][ek], self.h_k[p],
-                                                                  self.coordination(ek))
-                if key not in cache:
-                    cache[key] = np.asarray(self.edge_hamiltonian(p, ek), dtype=complex)
-                out[p, ek] = cache[key]
+                zi, zj = self.coordination(ek)
+                field = field_i / zi + field_j / zj
+                j = np.array([self.j_ij[p][ek] for p in plain])
+                out[plain, ek] = j[:, None, None] * interaction + h[:, None, None] * field
+        for p in range(self.n_points):
+            if self.hamiltonian[p] is not None:
+                out[p, :] = np.asarray(self.hamiltonian[p], dtype=complex)
         return out
 
     def _gates(self, hams, dts_of_point):
-        """expm(-dt H) per (point, edge); identical matrices are exponentiated once."""
-        out = np.empty_like(hams)
-        cache = {}
-        for p in range(hams.shape[0]):
-            for ek in range(hams.shape[1]):
-                key = (hams[p, ek].tobytes(), complex(dts_of_point[p]))
-                if key not in cache:
-                    cache[key] = linalg.expm(-dts_of_point[p] * hams[p, ek])
-                out[p, ek] = cache[key]
-        return out
+        """expm(-dt H) per (point, edge): the distinct (H, dt) pairs go through ONE stacked scipy.linalg.expm call,
+        which applies the same Pade routine per matrix (bit-identical to the reference's one-matrix calls, :470-473;
+        checked in tests/test_host.py)."""
+        n_p, m = hams.shape[:2]
+        index, uniq_h, uniq_dt = {}, [], []
+        which = np.empty((n_p, m), dtype=np.int64)
+        for p in range(n_p):
+            dt = complex(dts_of_point[p])
+            for ek in range(m):
+                key = (hams[p, ek].tobytes(), dt)
+                k = index.get(key)
+                if k is None:
+                    k = index[key] = len(uniq_h)
+                    uniq_h.append(hams[p, ek])
+                    uniq_dt.append(dts_of_point[p])
+                which[p, ek] = k
+        stack = np.array([-dt * h for dt, h in zip(uniq_dt, uniq_h)])
+        return linalg.expm(stack)[which]
 
     # ------------------------------------------------------------------ engine lifecycle
     def _current_dims(self):
@@ -162,11 +203,30 @@ class SimpleUpdateBatch:
             self._gates_key = None
             self._hams_uploaded = False
         self._hams = hams
-        if not self._hams_uploaded:
+        if not self._hams_uploaded or self._hams_uploaded_obj is not hams:
             eng.set_hamiltonians(hams)
-            self._hams_uploaded = True
-        self.upload_state()
+            self._hams_uploaded, self._hams_uploaded_obj = True, hams
+        if not self._state_in_sync():
+            self.upload_state()
         return eng
+
+    def _state_in_sync(self):
+        """True when every tensor / weight array object is the one last uploaded to or downloaded from the device.
+        The reference replaces list entries when it updates (:294-296); in-place edits of an array are NOT seen —
+        replace the entry or call upload_state()."""
+        refs = getattr(self, "_synced", None)
+        if refs is None or self._synced_engine is not self._engine:
+            return False
+        for tn, (ts, ws) in zip(self.tensor_networks, refs):
+            if len(tn.tensors) != len(ts) or len(tn.weights) != len(ws):
+                return False
+            if any(a is not b for a, b in zip(tn.tensors, ts)) or any(a is not b for a, b in zip(tn.weights, ws)):
+                return False
+        return True
+
+    def _mark_synced(self):
+        self._synced = [(list(tn.tensors), list(tn.weights)) for tn in self.tensor_networks]
+        self._synced_engine = self._engine
 
     def upload_state(self):
         eng = self._engine
@@ -176,6 +236,7 @@ class SimpleUpdateBatch:
             eng.set_tensor(t, stacked if eng.complex else np.real(stacked))
         for e in range(m):
             eng.set_weights(e, np.stack([np.asarray(tn.weights[e], dtype=float) for tn in self.tensor_networks]))
+        self._mark_synced()
 
     def download_state(self):
         """Write the device state back into the TensorNetwork objects (complex128 tensors, as the
@@ -190,9 +251,10 @@ class SimpleUpdateBatch:
             vals = eng.get_weights(e)
             for p, tn in enumerate(self.tensor_networks):
                 tn.weights[e] = np.array(vals[p])
+        self._mark_synced()
 
     def _set_schedule_gates(self):
-        key = ("schedule", tuple(tuple(complex(x) for x in d) for d in self.dts))
+        key = ("schedule", tuple(tuple(complex(x) for x in d) for d in self.dts), id(self._hams))
         if self._gates_key == key:
             return
         n_dts = len(self.dts[0])
@@ -309,9 +371,7 @@ class SimpleUpdate:
             if b._engine is not None and b._engine.n_slots != len(self.dts) + 1:
                 b._engine.reserve_gate_slots(len(self.dts) + 1)
         b.d_max, b.max_iterations, b.convergence_error = self.d_max, self.max_iterations, self.convergence_error
-        b._hams_uploaded = False  # Hamiltonian parameters may have changed; the upload is tiny
-        b._gates_key = None
-        return b
+        return b  # changed parameters are picked up by value (SimpleUpdateBatch._params_key)
 
     # ---- run loop (:107-194) ----
     def run(self):

@@ -160,3 +160,19 @@ def test_partition_round_robin():
         partition(4, 2, 2)
     vals = np.arange(7.0)
     assert np.array_equal(gather_points(vals, 7, 1, 0)[:, 0], vals)
+
+
+def test_stacked_expm_is_bit_identical_to_single_calls():
+    """SimpleUpdateBatch._gates exponentiates all distinct (H, dt) pairs in one stacked scipy.linalg.expm call; the
+    reference calls expm once per edge (simple_update.py:470-473).  Same Pade routine per matrix: identical bits."""
+    from scipy import linalg
+
+    pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
+    hams = np.array([(-np.kron(pz, pz) + h * (np.kron(px, np.eye(2)) + np.kron(np.eye(2), px)) / 4).astype(complex)
+                     for h in -np.linspace(0, 4, 33)])
+    rng = np.random.default_rng(0)
+    herm = rng.normal(size=(7, 9, 9)) + 1j * rng.normal(size=(7, 9, 9))
+    herm = herm + np.conj(np.transpose(herm, (0, 2, 1)))
+    for stack in (hams, herm):
+        for dt in (0.1, 0.001, 0.05j):
+            assert np.array_equal(linalg.expm(-dt * stack), np.array([linalg.expm(-dt * h) for h in stack]))

@@ -252,6 +252,34 @@ def test_size_independent_properties_at_full_size(tnsu):
     assert np.isfinite(e0)
 
 
+def test_host_edits_reach_the_device(tnsu):
+    """The wrapper re-uploads when a list entry of the TensorNetwork or a model parameter was replaced between calls
+    (the reference reads tensors / weights / j_ij / h_k at call time)."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("star")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    np.random.seed(3)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=3, spin_dim=2)
+    su = tnsu.SimpleUpdate(tn, [1.0] * 9, 0.0, [sx, sy, sz], [sx, sy, sz], [sz], [0.1], d_max=3, print_process=False)
+    su.simple_update()
+
+    def oracle_energy():
+        model = orc.Model(su.j_ij, su.h_k, su.s_i, su.s_j, su.s_k)
+        return orc.energy_per_site([np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights], smat, model)
+
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    tn.weights[2] = np.array([0.7, 0.2, 0.1])          # replaced weight vector
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    tn.tensors[1] = tn.tensors[1] + 0.05               # replaced tensor
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    su.h_k = 0.3                                       # changed field
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    su.j_ij = [0.5] * 9                                # changed couplings
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    su.simple_update()                                 # and the update sees them too
+    t0, w0 = [np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights]
+    assert all(abs(np.linalg.norm(t) - 1) < 1e-12 for t in t0) and abs(su.energy_per_site() - oracle_energy()) < 1e-12
+
+
 def test_engine_error_paths(tnsu):
     smat = tnsu.smc.infinite_structure_matrix_dict("chain")
     with pytest.raises(tnsu.EngineError, match="UNSUPPORTED"):
