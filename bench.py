@@ -324,6 +324,19 @@ def run_gpu_arm(args):
     gpu_launches = eng.launch_count - launches0
     prof = eng.profile_sweep(0)  # one extra sweep with events between the kernel classes (not part of `value`)
 
+    # ---- energy_per_site over the resident batch: the bandwidth-bound pair-RDM contraction (reference :525-637) ----
+    eng.energy()
+    eng.energy()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ee0.record(stream)
+    for _ in range(args.energy_steps):
+        en_vals = eng.energy()  # launches pair_rdm + pair_sum, copies B energies to the host, synchronises
+    ee1.record(stream)
+    barrier()
+    energy_ms = ee0.elapsed_time(ee1) / args.energy_steps
+    assert np.all(np.isfinite(en_vals))
+
     # ---- end to end through the API with host buffers ----
     # The batch is split over `e2e_chunks` engines (handles are independent: one stream each) driven by one host
     # thread each, so the pinned-memory upload of one chunk overlaps the sweep of another.
@@ -377,10 +390,10 @@ def run_gpu_arm(args):
         pe.close()
 
     # ---- max over ranks ----
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms, e2e_s * 1e3, energy_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = (float(x) for x in times.cpu())
+    ms, e2e_ms, energy_ms = (float(x) for x in times.cpu())
     edges_per_step = world * batch * N_E
     value = edges_per_step * args.steps / (ms * 1e-3)
     e2e_value = edges_per_step * args.e2e_steps / (e2e_ms * 1e-3)
@@ -434,6 +447,25 @@ def run_gpu_arm(args):
             "clocks": clocks.summary(),
             "kernel_ms_per_sweep": prof,
         }
+        # energy_per_site: HBM roofline on the MINIMAL bytes (every site tensor read once per evaluation);
+        # the reference-shaped figure reads both tensors of every edge (4x at z = 4; the re-reads hit L2 here)
+        en_min = batch * (N_T * D * DIM ** 4 * sbytes + N_E * DIM * 8 + 8)
+        en_ref = batch * N_E * (2 * D * DIM ** 4 * sbytes + 7 * DIM * 8)
+        en_gbs = en_min / (energy_ms * 1e-3) / 1e9
+        mb = (D * DIM + 7) // 8
+        dmma_flop = batch * N_E * 2 * (mb * (mb + 1) // 2) * (DIM ** 3 // 4) * 512  # executed m8n8k4 DMMAs x 2*8*8*4
+        line["energy"] = {
+            "metric": "energy_per_site evaluations/s (peps D=8: 8 pair RDMs + <H> each), state resident in HBM",
+            "value": world * batch / (energy_ms * 1e-3), "unit": "evaluations/s", "ms_per_batch": energy_ms,
+            "pair_rdms_per_s": world * batch * N_E / (energy_ms * 1e-3), "steps": args.energy_steps,
+            "roofline": {"bound": "hbm", "achieved": en_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": en_gbs / pk["hbm_gbs"], "algorithmic_bytes_per_launch": en_min,
+                         "reference_shaped_bytes_per_launch": en_ref,
+                         "reference_shaped_gbs": en_ref / (energy_ms * 1e-3) / 1e9,
+                         "kernel": "pair_rdm_dmma_kernel<2> (+ pair_sum_kernel, 71 KB D2H)" if not cplx else "pair_rdm_kernel<cplx>",
+                         "dmma_tflops": None if cplx else dmma_flop / (energy_ms * 1e-3) / 1e12,
+                         "dmma_peak_tflops_measured": 37.0},
+        }
         if sweep is not None:
             if args.sweep_cpu_points > 0:
                 sec, picks = tfi_sweep_cpu(args.sweep_cpu_points, args.sweep_points)
@@ -456,6 +488,7 @@ def main():
     ap.add_argument("--sweep-cpu-points", type=int, default=2, help="points of the sweep the oracle runs for the CPU baseline")
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--energy-steps", type=int, default=10)
     ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")

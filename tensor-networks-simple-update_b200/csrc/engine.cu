@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/tnsu_b200.h"
@@ -77,6 +78,7 @@ struct tnsu_engine {
   bool svd_precond = true;                // TNSU_SVD_PRECOND=0: plain Jacobi in the warp SVD (A/B comparisons)
   bool use_graphs = false;                // TNSU_GRAPH=1: replay the run-loop iteration as a CUDA graph (measured: no faster)
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
+  bool force_simple_rdm = false;          // TNSU_RDM=simple: shared-memory-staged pair RDM kernel instead of the DMMA one (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
@@ -489,6 +491,23 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
   p.rdm_out = rdm_out;
   p.iter_state = iter_state;
   p.active = active;
+  if constexpr (std::is_same<S, double>::value) {
+    if (!e->force_simple_rdm && e->dcap <= PG_WL) {
+      // real path: Gram matrices on the FP64 tensor cores, operands straight from HBM/L2 (rdm.cuh)
+      const int MB = (maxM + 7) / 8;
+      const int smem_d = pair_dmma_smem_bytes(MB, e->d4);
+      const int grid = e->batch * n_list;
+      switch (MB) {
+        case 1: pair_rdm_dmma_kernel<1><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
+        case 2: pair_rdm_dmma_kernel<2><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
+        case 3: pair_rdm_dmma_kernel<3><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
+        default: pair_rdm_dmma_kernel<4><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
+      }
+      CK(cudaGetLastError());
+      e->launches++;
+      return TNSU_OK;
+    }
+  }
   int smem = pair_smem_bytes(e, maxM);
   if (smem > SMEM_LIMIT) return fail(e, TNSU_E_UNSUPPORTED, "pair RDM needs %d bytes of shared memory", smem);
   static bool attr_done = false;
@@ -743,6 +762,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     if (env) e->force_ncols = atoi(env);
     env = getenv("TNSU_LQ");
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
+    env = getenv("TNSU_RDM");
+    e->force_simple_rdm = env && std::string(env) == "simple";
   }
   e->n = n;
   e->m = m;

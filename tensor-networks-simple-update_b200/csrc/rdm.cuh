@@ -177,6 +177,275 @@ __global__ void __launch_bounds__(RDM_THREADS) pair_rdm_kernel(const PairRdmLaun
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Real-FP64 fast path: the two Gram matrices on the FP64 tensor cores (DMMA m8n8k4), operands loaded
+// straight from HBM/L2 into the mma fragment layout — no staging of the tensor in shared memory.
+//
+// G[r][r'] = sum_c P[r][c] w_c P[r'][c] is a SYRK with M = d*D_k <= 32 rows and N = prod(other dims)
+// columns.  For m8n8k4 the A fragment (row-major 8x4: lane holds A[lane/4][lane%4]) and the B fragment
+// (col-major 4x8: lane holds B[lane%4][lane/4]) of a Gram product are the SAME register when the row
+// block is the same, so one load per (8-row block, 4 columns) feeds every tile of that block: MB loads
+// and MB(MB+1)/2 DMMAs per k-step (the strictly upper blocks follow by symmetry).  Warps 0-3 take
+// tensor i, warps 4-7 tensor j, each one k-step out of four; the four partial fragments of a side are
+// summed in a fixed order (deterministic).  Column offsets and the squared environment weights come
+// from a per-chunk table in shared memory built once per CTA.
+// CTAs of one point are adjacent in the grid, so a site tensor shared by several edges is read from
+// DRAM once and from L2 afterwards.
+// ---------------------------------------------------------------------------------------------
+#define PG_THREADS 256
+#define PG_CHUNK 512  // columns per side and pass
+#define PG_UNROLL 4   // k-steps in flight per warp
+#define PG_WL 32      // leading dimension of the per-leg weight table (D <= 16 whenever d*D <= 32)
+
+DEV void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct __align__(16) PgCol {  // one column of the bond matrix: squared environment weight and element offset
+  double w;
+  int off;
+  int pad;
+};
+struct __align__(16) PgLeg {  // one environment leg: dimension, 2^32/dim rounded up (exact division of c < 2^20), stride
+  int dim;
+  unsigned magic;
+  int stride;
+  int pad;
+};
+
+static inline int pair_dmma_smem_bytes(int MB, int d4) {
+  const int MP = 8 * MB;
+  return 2 * MP * MP * 8 + 2 * PG_CHUNK * 16 + 2 * TNSU_MAX_LEGS * 16 + 2 * TNSU_MAX_LEGS * PG_WL * 8 + MP * 8 + d4 * 8 + 64;
+}
+
+template <int MB>
+__global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_kernel(const PairRdmLaunch<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int MP = 8 * MB;
+  constexpr int NBLK = MB * (MB + 1) / 2;
+  const int b = blockIdx.x / p.n_list;
+  const int ek = p.edge_list[blockIdx.x - b * p.n_list];
+  if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.iter_state != nullptr) {
+    const int it = p.iter_state[b];
+    if (!(it % 2 == 0 && it > 0)) return;
+  }
+  const EdgeDesc &ed = p.descs[ek];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int side = warp >> 2, q = warp & 3, g = lane >> 2, t = lane & 3;
+  const int d = ed.d, Dk = ed.Dk, M = d * Dk;
+
+  PgCol *cols = (PgCol *)smem_raw;                           // [2][PG_CHUNK]
+  PgLeg *legs = (PgLeg *)(cols + 2 * PG_CHUNK);              // [2][legs]: environment legs, innermost first
+  double *gram = (double *)(legs + 2 * TNSU_MAX_LEGS);       // [2][MP][MP]
+  double *wsq = gram + 2 * MP * MP;                          // [2][legs][PG_WL] squared weights, same order as `legs`
+  double *lamrow = wsq + 2 * TNSU_MAX_LEGS * PG_WL;          // [MP] lambda_k of the bond index of row r
+  double *rho = lamrow + MP;                                 // [d4]
+  double *red = rho + p.d4;
+
+  const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
+  // environment legs of both sides, innermost first (the order in which a column index is decoded)
+  for (int idx = tid; idx < 2 * TNSU_MAX_LEGS * PG_WL; idx += PG_THREADS) {
+    const int sdx = idx / (TNSU_MAX_LEGS * PG_WL), k = (idx / PG_WL) % TNSU_MAX_LEGS, x = idx % PG_WL;
+    const SideDesc &s2 = ed.s[sdx];
+    int l = s2.nlegs - 1 - k;          // k-th environment leg from the inside: skip the bond leg
+    if (l <= s2.bond_leg) --l;
+    double w = 1.0;
+    if (l >= 0) {
+      const int dim = s2.dims[l];
+      if (x < dim) w = wpoint[(size_t)s2.leg_edge[l] * p.dcap + x];
+      if (x == 0) {
+        PgLeg L;
+        L.dim = dim;
+        L.magic = dim > 1 ? 0xFFFFFFFFu / (unsigned)dim + 1u : 0u;
+        L.stride = (int)s2.in_stride[l];
+        L.pad = 0;
+        legs[sdx * TNSU_MAX_LEGS + k] = L;
+      }
+    }
+    wsq[idx] = w * w;
+  }
+  if (tid < MP) lamrow[tid] = tid < M ? wpoint[(size_t)ek * p.dcap + tid % Dk] : 0.0;
+
+  const SideDesc &sd = ed.s[side];
+  // pull both site tensors towards L2 while the column table is being built (each is one contiguous block)
+  {
+    const char *tb = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride);
+    const long long bytes = (long long)M * sd.N * 8;
+    for (long long o = (long long)(tid & 127) * 128; o < bytes; o += 128 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + o));
+  }
+  // rows past M are clamped to row 0: their Gram entries are computed and never read
+  const char *rowp[MB];
+#pragma unroll
+  for (int I = 0; I < MB; ++I) {
+    const int r = 8 * I + g < M ? 8 * I + g : 0;
+    const int s = r / Dk, x = r - s * Dk;
+    rowp[I] = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride + (long long)s * sd.in_stride_phys +
+                             (long long)x * sd.in_stride[sd.bond_leg]);
+  }
+  double acc[NBLK][2];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) acc[k][0] = acc[k][1] = 0.0;
+
+  const int nenv0 = ed.s[0].nlegs - 1, nenv1 = ed.s[1].nlegs - 1;
+  const int N0 = ed.s[0].N, N1 = ed.s[1].N;
+  const int Nmax = max(N0, N1);
+  constexpr int KSTEP_GROUP = 4 * PG_UNROLL;  // k-steps per trip of the four warps of a side
+  for (int c0 = 0; c0 < Nmax; c0 += PG_CHUNK) {
+    __syncthreads();  // legs / wsq ready, previous chunk consumed
+    for (int idx = tid; idx < 2 * PG_CHUNK; idx += PG_THREADS) {
+      const int sdx = idx / PG_CHUNK, cc = idx - sdx * PG_CHUNK;  // uniform per warp
+      const int Ns = sdx ? N1 : N0;
+      const int left = Ns - c0;
+      if (left <= 0) continue;
+      const int nks_pad = (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP;
+      if (cc >= 4 * nks_pad) continue;
+      PgCol e;
+      e.w = 0.0;
+      e.off = 0;
+      e.pad = 0;
+      if (cc < left) {
+        const PgLeg *lg = legs + sdx * TNSU_MAX_LEGS;
+        const double *wl = wsq + sdx * TNSU_MAX_LEGS * PG_WL;
+        const int nenv = sdx ? nenv1 : nenv0;
+        unsigned rem = (unsigned)(c0 + cc);
+        double w = 1.0;
+        unsigned off = 0;
+        for (int k = 0; k < nenv; ++k) {
+          const PgLeg L = lg[k];
+          const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
+          const unsigned x = rem - qq * (unsigned)L.dim;
+          rem = qq;
+          off += x * (unsigned)L.stride;
+          w *= wl[k * PG_WL + x];
+        }
+        e.w = w;
+        e.off = (int)(off * 8u);  // byte offset
+      }
+      cols[idx] = e;
+    }
+    __syncthreads();
+    const int left = sd.N - c0;
+    if (left > 0) {
+      const int nks_pad = (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP;
+      const PgCol *cl = cols + side * PG_CHUNK + t;
+      // software pipeline: the loads of trip n+1 are in flight while the DMMAs of trip n issue
+      double v[PG_UNROLL][MB], w[PG_UNROLL];
+#pragma unroll
+      for (int u = 0; u < PG_UNROLL; ++u) {
+        const PgCol e = cl[4 * (q + 4 * u)];
+        w[u] = e.w;
+#pragma unroll
+        for (int I = 0; I < MB; ++I) v[u][I] = __ldg((const double *)(rowp[I] + (unsigned)e.off));
+      }
+#pragma unroll 1
+      for (int ks0 = q; ks0 < nks_pad; ks0 += KSTEP_GROUP) {
+        double vn[PG_UNROLL][MB], wn[PG_UNROLL];
+        const int ksn = ks0 + KSTEP_GROUP < nks_pad ? ks0 + KSTEP_GROUP : ks0;  // last trip reloads itself (L1 hit)
+#pragma unroll
+        for (int u = 0; u < PG_UNROLL; ++u) {
+          const PgCol e = cl[4 * (ksn + 4 * u)];
+          wn[u] = e.w;
+#pragma unroll
+          for (int I = 0; I < MB; ++I) vn[u][I] = __ldg((const double *)(rowp[I] + (unsigned)e.off));
+        }
+#pragma unroll
+        for (int u = 0; u < PG_UNROLL; ++u) {
+          int k = 0;
+#pragma unroll
+          for (int I = 0; I < MB; ++I) {
+            const double a = v[u][I] * w[u];
+#pragma unroll
+            for (int J = 0; J <= I; ++J, ++k) dmma884(acc[k][0], acc[k][1], a, v[u][J]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PG_UNROLL; ++u) {
+          w[u] = wn[u];
+#pragma unroll
+          for (int I = 0; I < MB; ++I) v[u][I] = vn[u][I];
+        }
+      }
+    }
+  }
+  // sum the four partial fragments of each side in warp order; tile (I,J) element [g][2t+{0,1}]
+  double *gs = gram + side * MP * MP;
+  for (int wv = 0; wv < 4; ++wv) {
+    __syncthreads();
+    if (q == wv) {
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < MB; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J, ++k) {
+          double2 *dst = (double2 *)(gs + (8 * I + g) * MP + 8 * J + 2 * t);
+          double2 cur = make_double2(0.0, 0.0);
+          if (wv != 0) cur = *dst;
+          cur.x += acc[k][0];
+          cur.y += acc[k][1];
+          *dst = cur;
+        }
+    }
+  }
+  __syncthreads();
+  // strictly upper blocks by symmetry; G_j picks up lambda_e lambda_f on its bond indices
+  for (int idx = tid; idx < 2 * MP * MP; idx += PG_THREADS) {
+    const int sdx = idx / (MP * MP), rest = idx - sdx * MP * MP;
+    const int r = rest / MP, c = rest - r * MP;
+    if ((r >> 3) >= (c >> 3)) {
+      double v = gram[idx];
+      if (sdx) v *= lamrow[r] * lamrow[c];
+      gram[idx] = v;
+      if ((r >> 3) > (c >> 3)) gram[sdx * MP * MP + c * MP + r] = v;
+    }
+  }
+  __syncthreads();
+
+  // rho[i,j,i',j'] = sum_{e,f} G_i[(i,e),(i',f)] (lam_e lam_f G_j[(j,e),(j',f)]): one warp per entry, lanes over (e,f)
+  const double *gi = gram, *gj = gram + MP * MP;
+  int eo[8];  // (e,f) pairs of this lane as offsets e*MP + f; Dk <= 16 -> at most 8 per lane
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ef = lane + 32 * k;
+    const int e = ef / Dk, f = ef - e * Dk;
+    eo[k] = ef < Dk * Dk ? e * MP + f : -1;
+  }
+  for (int idx = warp; idx < p.d4; idx += PG_THREADS / 32) {
+    const int jp = idx % d, ip = (idx / d) % d, j = (idx / (d * d)) % d, i = idx / (d * d * d);
+    const double *bi = gi + (i * Dk) * MP + ip * Dk, *bj = gj + (j * Dk) * MP + jp * Dk;
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (eo[k] >= 0) a = fma(bi[eo[k]], bj[eo[k]], a);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+    if (lane == 0) rho[idx] = a;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double tr = 0.0;
+    for (int ij = lane; ij < d * d; ij += 32) tr += rho[ij * d * d + ij];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, m);
+    if (lane == 0) red[0] = 1.0 / tr;
+  }
+  __syncthreads();
+  const double itr = red[0];
+  if (p.rdm_out != nullptr && ek == p.edge_list[0])
+    for (int idx = tid; idx < p.d4; idx += PG_THREADS) p.rdm_out[(size_t)b * p.d4 + idx] = mkc(rho[idx] * itr, 0.0);
+  if (p.pair_val != nullptr && warp == 0) {
+    const double *op = p.ops + (size_t)b * p.op_point_stride + (size_t)ek * p.op_edge_stride;
+    double v = 0.0;
+    for (int idx = lane; idx < p.d4; idx += 32) v = fma(rho[idx] * itr, op[idx], v);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) p.pair_val[(size_t)b * p.m_edges + ek] = mkc(v, 0.0);
+  }
+}
+
 // energy[b] = Re( sum_e pair_val[b][e] ) / n_tensors; cval[b] keeps the complex sum / n.
 __global__ void pair_sum_kernel(const cplx *pair_val, int batch, int m_edges, int n_tensors, double *energy,
                                 cplx *cval, const int *iter_state, const int *active) {

@@ -193,6 +193,40 @@ def test_svd_kernels_agree(tnsu, monkeypatch):
         assert abs(e - results[0][1]) < 1e-12
 
 
+@pytest.mark.parametrize("lattice,dim,d", [("peps", 8, 2), ("star", 2, 2), ("triangle", 4, 3), ("peps", 16, 2), ("peps", 5, 3),
+                                           ("chain", 6, 2), ("obc4x3", 3, 2)])
+def test_pair_rdm_kernels_agree(tnsu, monkeypatch, lattice, dim, d):
+    """The tensor-core (DMMA) pair-RDM kernel of the real path and the shared-memory-staged one (TNSU_RDM=simple)
+    give the same pair RDMs and energy, and both match the oracle (reference simple_update.py:525-593, :615-637):
+    1, 2, 3 and 4 row blocks of 8, ragged legs (open boundaries), more columns than one table chunk (D=16)."""
+    if lattice == "obc4x3":
+        smat = tnsu.smc.rectangular_peps_obc(4, 3)
+    else:
+        smat = tnsu.smc.infinite_structure_matrix_dict(lattice)
+    sx, sy, sz = tnsu.spin_operators((d - 1) / 2.0)
+    m = smat.shape[1]
+    results = []
+    for env in ("", "simple"):
+        monkeypatch.delenv("TNSU_RDM", raising=False)
+        if env:
+            monkeypatch.setenv("TNSU_RDM", env)
+        np.random.seed(33)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim, spin_dim=d)
+        tn.weights = [np.sort(np.random.uniform(0.05, 1.0, dim))[::-1] for _ in range(m)]
+        su = tnsu.SimpleUpdate(tn, [1.0] * m, 0.3, [sx, sy, sz], [sx, sy, sz], [sz], [0.1], d_max=dim, print_process=False)
+        rdms = [np.array(su.tensor_pair_rdm(e)) for e in (0, m // 2, m - 1)]
+        results.append((su.energy_per_site(), rdms))
+        if not env:
+            model = orc.Model([1.0] * m, 0.3, [sx, sy, sz], [sx, sy, sz], [sz])
+            e_ref = orc.energy_per_site(tn.tensors, tn.weights, smat, model)
+            assert abs(results[0][0] - e_ref) < TOL_E * max(1.0, abs(e_ref))
+            for e, r in zip((0, m // 2, m - 1), rdms):
+                assert np.abs(r - orc.pair_rdm(tn.tensors, tn.weights, smat, e)).max() < 1e-12
+    assert abs(results[0][0] - results[1][0]) < 1e-12 * max(1.0, abs(results[1][0]))
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.abs(a - b).max() < 1e-12
+
+
 def test_batch_matches_single_and_oracle(tnsu):
     """A batch of TFI points with different fields: every point equals its own single-network run and the
     oracle, i.e. batching does not couple points."""
