@@ -5,7 +5,7 @@
 
 One "step" = one Simple-Update sweep (8 edge updates: absorb, QR reduction, gate, truncated SVD,
 renormalise) over a batch of B independent random-init networks of BASELINE.json configs[1]
-(d=2, virtual_dim = d_max = 8, j_ij=1, h_k=0, dt=0.1, seed b for network b).  B (default 8880 per GPU) is chosen
+(d=2, virtual_dim = d_max = 8, j_ij=1, h_k=0, dt=0.1, seed b for network b).  B (default 9472 per GPU) is chosen
 so the state (B x 4 tensors x 8192 float64 = B x 256 KiB = 2.2 GiB) is far larger than the 126 MB L2.
 
   value  edge-updates/s with the state resident in HBM (CUDA events on the engine's stream, max over ranks)
@@ -482,8 +482,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8880,
-                    help="networks per GPU; 8880 = 5 x 148 SMs x 12 resident SVD warps, so the K2 grid is whole waves")
+    ap.add_argument("--batch", type=int, default=9472,
+                    help="networks per GPU; 9472 = 4 x 148 SMs x 16 resident SVD warps, so the K2 grid is whole waves")
     ap.add_argument("--sweep-points", type=int, default=256, help="points of the TFI sweep (Metric 2); 0 skips it")
     ap.add_argument("--sweep-cpu-points", type=int, default=2, help="points of the sweep the oracle runs for the CPU baseline")
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")

@@ -199,8 +199,37 @@ def svd_preconditioned(theta):
     return u, sv, acc.T, sweeps
 
 
-def edge_update(tensors, weights, smat, ek, gate, d_max):
-    """Same contract as tnsu_oracle.edge_update, computed the way the kernel does."""
+def svd_vfree(theta, keep):
+    """The default K2 route (svd_warp_kernel<R, false>): pivoted QR of theta^T, odd-even Jacobi on X = R~^T WITHOUT
+    an accumulator, the `keep` largest columns give sigma and u = x / sigma; the matching right vectors are recovered
+    from theta itself, w = theta^T u / ||theta^T u|| (a fixed dense start vector when that is zero), followed by two
+    passes of modified Gram-Schmidt in rank order.  Returns u (n_i x keep), s (keep), w^T (keep x n_j), sweeps."""
+    theta = np.array(theta, dtype=float)
+    _, r_tilde = qr_column_pivoting(theta.T)
+    x, _, sweeps = jacobi_odd_even(r_tilde.T, np.zeros((1, r_tilde.shape[0])))
+    sv = np.sqrt(np.sum(x * x, axis=0))
+    order = np.argsort(-sv, kind="stable")[:keep]
+    sv, x = sv[order], x[:, order]
+    u = x * np.where(sv > 0, 1.0 / np.where(sv > 0, sv, 1.0), 0.0)
+    w = theta.T @ u
+    for j in range(w.shape[1]):
+        if not np.sum(w[:, j] ** 2) > 1e-280:
+            c = np.arange(1, w.shape[0] + 1, dtype=np.uint64)
+            h = ((c * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) ^ np.uint64(((j + 1) * 40503) & 0xFFFFFFFF)
+            w[:, j] = ((h >> np.uint64(8)) & np.uint64(0xFFFF)).astype(float) - 32767.5
+    for _ in range(2):
+        for j in range(w.shape[1]):
+            n2 = np.sum(w[:, j] ** 2)
+            if n2 > 0:
+                w[:, j] /= np.sqrt(n2)
+            for i in range(j + 1, w.shape[1]):
+                w[:, i] -= (w[:, i] @ w[:, j]) * w[:, j]
+    return u, sv, w.T, sweeps
+
+
+def edge_update(tensors, weights, smat, ek, gate, d_max, vfree=False):
+    """Same contract as tnsu_oracle.edge_update, computed the way the kernel does (`vfree`: the V-free SVD route
+    of the real-float64 warp kernel instead of the accumulating Jacobi)."""
     ti, ai, tj, aj = edge_endpoints(smat, ek)
     lam = weights[ek]
     sides = []
@@ -215,9 +244,15 @@ def edge_update(tensors, weights, smat, ek, gate, d_max):
     r_i = np.reshape(l_i, (d_i, dk, k_i))
     r_j = np.reshape(l_j, (d_j, dk, k_j))
     theta = np.einsum("ieq,e,jep,ijab->qabp", r_i, lam, r_j, gate)
-    u, s, vh = jacobi_svd(np.reshape(theta, (k_i * d_i, d_j * k_j)))
-    d_new = min(d_max, len(s)) if d_max is not None else len(s)
-    u, s, vh = u[:, :d_new], s[:d_new], vh[:d_new, :]
+    th2 = np.reshape(theta, (k_i * d_i, d_j * k_j))
+    if vfree:
+        full = min(th2.shape)
+        d_new = min(d_max, full) if d_max is not None else full
+        u, s, vh, _ = svd_vfree(np.real(th2), d_new)
+    else:
+        u, s, vh = jacobi_svd(th2)
+        d_new = min(d_max, len(s)) if d_max is not None else len(s)
+        u, s, vh = u[:, :d_new], s[:d_new], vh[:d_new, :]
     rt_i = np.reshape(np.transpose(np.reshape(u, (k_i, d_i, d_new)), (1, 2, 0)), (d_i * d_new, k_i))
     rt_j = np.reshape(np.transpose(np.reshape(vh, (d_new, d_j, k_j)), (1, 0, 2)), (d_j * d_new, k_j))
     for t, a, rt, yh, t_mat, sh in ((ti, ai, rt_i, yh_i, t_i, sh_i), (tj, aj, rt_j, yh_j, t_j, sh_j)):

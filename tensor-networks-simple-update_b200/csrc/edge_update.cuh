@@ -78,6 +78,8 @@ struct EdgeLaunch {
   int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
   int svdw_precond;          // pivoted-QR preconditioner before the Jacobi iteration
   int svdw_ldt;              // leading dimension of its transpose buffer
+  int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
+  int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;
   // debug dump (tnsu_debug_edge)
   double *dbg_sigma;

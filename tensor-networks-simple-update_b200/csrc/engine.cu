@@ -26,7 +26,7 @@ struct LevelCfg {
   int nt = 32;       // threads per side CTA
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
-  int svdw_precond = 0, svdw_ldt = 0;
+  int svdw_precond = 0, svdw_ldt = 0, svdw_accv = 1, svdw_tb_off = 0;
   int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
   int cluster = 1;                                                   // CTAs per (item, side) in K1 / K3
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
@@ -78,6 +78,7 @@ struct tnsu_engine {
   bool svd_precond = true;                // TNSU_SVD_PRECOND=0: plain Jacobi in the warp SVD (A/B comparisons)
   bool use_graphs = false;                // TNSU_GRAPH=1: replay the run-loop iteration as a CUDA graph (measured: no faster)
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
+  bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
   bool force_simple_rdm = false;          // TNSU_RDM=simple: shared-memory-staged pair RDM kernel instead of the DMMA one (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
@@ -290,6 +291,20 @@ static int plan_sweep(tnsu_engine *e) {
         c.svdw_np = std::max(1, (maxnr + 1) / 2);
         c.svdw_ldt = std::max(2 * c.svdw_np, 2 * c.svdw_rows) | 1;
         c.svdw_group_doubles = 2 * ldm2 + e->d4 + e->dcap + 2 * c.svdw_rows * c.svdw_ldt + 2 * c.svdw_rows + 2;
+        if (!e->svd_accumulate_v) {
+          // V-free iteration: theta (2R x 2NP, column-major) stays in place; the half-size transpose buffer and the
+          // pivot column go on the dead L_i / L_j when they fit, else behind theta
+          c.svdw_accv = 0;
+          const int tb = c.svdw_rows * c.svdw_ldt + 2 * c.svdw_rows + 2;
+          const int th = 2 * c.svdw_rows * 2 * c.svdw_rows;  // read without bounds at the end: full 2R x 2R, zero padded
+          if (tb <= 2 * ldm2) {
+            c.svdw_tb_off = 0;
+            c.svdw_group_doubles = 2 * ldm2 + e->d4 + e->dcap + th;
+          } else {
+            c.svdw_tb_off = 2 * ldm2 + e->d4 + e->dcap + th;
+            c.svdw_group_doubles = c.svdw_tb_off + tb;
+          }
+        }
       }
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
@@ -414,6 +429,8 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_group_doubles = c.svdw_group_doubles;
     p.svdw_precond = c.svdw_precond;
     p.svdw_ldt = c.svdw_ldt;
+    p.svdw_accv = c.svdw_accv;
+    p.svdw_tb_off = c.svdw_tb_off;
     p.dbg_info = nullptr;
     if (dbg_point >= 0) {
       p.dbg_sigma = e->dbg_sigma;
@@ -762,6 +779,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     if (env) e->force_ncols = atoi(env);
     env = getenv("TNSU_LQ");
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
+    env = getenv("TNSU_SVD_V");
+    e->svd_accumulate_v = env && std::string(env) == "accumulate";
     env = getenv("TNSU_RDM");
     e->force_simple_rdm = env && std::string(env) == "simple";
   }

@@ -69,3 +69,45 @@ def test_preconditioned_odd_even_svd():
     a = rng.normal(size=(32, 32)) @ np.diag(np.logspace(0, -8, 32)) @ rng.normal(size=(32, 32))
     _, _, plain = dm.jacobi_odd_even(a, np.eye(32))
     assert dm.svd_preconditioned(a)[3] < plain
+
+
+@pytest.mark.parametrize("name", ["chain_growth", "obc4x3_D3", "peps_growth", "tfi_D4", "pbc3_D2_dt0"])
+def test_vfree_svd_route_matches_oracle(name):
+    """The default K2 route of the real path iterates A alone and recovers the kept right singular vectors from
+    theta afterwards (svd_warp_kernel<R, false>, device_model.svd_vfree).  Sweeps with that route agree with the
+    oracle's LAPACK route to 1e-12 on weights and energy, including bond growth (exactly rank-deficient thetas)."""
+    case = build_case(name)
+    smat = case["smat"]
+    np.random.seed(case["seed"])
+    tensors, weights = orc.random_network(smat, case["d"], case["virtual_dim"])
+    t2, w2 = [t.copy() for t in tensors], [w.copy() for w in weights]
+    model = orc.Model(case["j_ij"], case["h_k"], case["s_i"], case["s_j"], case["s_k"], case["hamiltonian"])
+    di, dj = model.dims
+    for _ in range(min(case["sweeps"], 3)):
+        orc.sweep(tensors, weights, smat, model, case["dt"], case["d_max"])
+        for ek in range(smat.shape[1]):
+            gate = orc.ite_gate(model.edge_hamiltonian(smat, ek), case["dt"], di, dj)
+            dm.edge_update(t2, w2, smat, ek, np.real(gate), case["d_max"], vfree=True)
+        for a, b in zip(weights, w2):
+            assert a.shape == b.shape and np.abs(a - b).max() < 1e-12
+        e1 = orc.energy_per_site(tensors, weights, smat, model)
+        e2 = orc.energy_per_site(t2, w2, smat, model)
+        assert abs(e1 - e2) < 1e-12
+
+
+def test_vfree_svd_properties():
+    """svd_vfree on graded and on exactly rank-deficient matrices: LAPACK's leading singular values, orthonormal kept
+    vectors on both sides, and theta w_k = sigma_k u_k wherever sigma_k is not negligible."""
+    rng = np.random.default_rng(5)
+    for shape, keep in (((32, 32), 8), ((16, 16), 4), ((24, 12), 6), ((12, 24), 6)):
+        a = rng.normal(size=shape) @ np.diag(np.logspace(0, -9, shape[1])) @ rng.normal(size=(shape[1], shape[1]))
+        u, s, wt, _ = dm.svd_vfree(a, keep)
+        ref = np.linalg.svd(a, compute_uv=False)[:keep]
+        assert np.abs(s - ref).max() < 1e-12 * ref[0]
+        assert np.abs(u.T @ u - np.eye(keep)).max() < 1e-12 and np.abs(wt @ wt.T - np.eye(keep)).max() < 1e-12
+        assert np.abs(a @ wt.T - u * s).max() < 1e-9 * ref[0]
+    a = np.outer(rng.normal(size=16), rng.normal(size=16)) + np.outer(rng.normal(size=16), rng.normal(size=16))  # rank 2
+    u, s, wt, _ = dm.svd_vfree(a, 6)
+    assert np.abs(s[:2] - np.linalg.svd(a, compute_uv=False)[:2]).max() < 1e-12 and s[2:].max() < 1e-12
+    assert np.abs(wt @ wt.T - np.eye(6)).max() < 1e-12
+    assert np.abs((u[:, :2] * s[:2]) @ wt[:2] - a).max() < 1e-12
