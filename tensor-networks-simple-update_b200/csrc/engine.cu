@@ -27,6 +27,7 @@ struct LevelCfg {
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
   int svdw_precond = 0, svdw_ldt = 0, svdw_accv = 1, svdw_tb_off = 0;
+  int rc_mout = 0, rc_k = 0, rc_ncl = 0;  // tensor-core K3 (recompose_dmma.cuh): largest Mout, K and slice width; 0 = not used
   int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
   int cluster = 1;                                                   // CTAs per (item, side) in K1 / K3
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
@@ -79,6 +80,7 @@ struct tnsu_engine {
   bool use_graphs = false;                // TNSU_GRAPH=1: replay the run-loop iteration as a CUDA graph (measured: no faster)
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
+  bool force_simple_rc = false;           // TNSU_RC=simple: register-column K3 (recompose_kernel) instead of the tensor-core one (A/B comparisons)
   bool force_simple_rdm = false;          // TNSU_RDM=simple: shared-memory-staged pair RDM kernel instead of the DMMA one (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
@@ -308,6 +310,17 @@ static int plan_sweep(tnsu_engine *e) {
       }
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
+    if (!cx && !e->force_simple_rc && e->dcap <= 32) {
+      int mo = 1, kk = 1;
+      for (int ek : e->level_edges[lv])
+        for (int s2 = 0; s2 < 2; ++s2) {
+          mo = std::max(mo, e->h_descs[ek].s[s2].Mout);
+          kk = std::max(kk, e->h_descs[ek].s[s2].K);
+        }
+      c.rc_mout = mo;
+      c.rc_k = kk;
+      c.rc_ncl = (maxN + c.cluster - 1) / c.cluster;
+    }
     if (std::max(c.smem_lq, std::max(c.smem_svd, c.smem_rc)) > SMEM_LIMIT)
       return fail(e, TNSU_E_UNSUPPORTED, "edge update needs %d bytes of shared memory", std::max(c.smem_lq, c.smem_svd));
     e->cfgs[lv] = c;
@@ -372,6 +385,16 @@ static cudaError_t launch_side_kernel(bool recompose, const LevelCfg &c, const E
 }
 
 cudaError_t launch_svd_warp_dispatch(const EdgeLaunch<double> &p, int n_items, cudaStream_t st);  // svdw_inst.cu
+cudaError_t launch_recompose_dmma_dispatch(const EdgeLaunch<double> &p, int n_items, int mout_max, int k_max, int ncl_cap,
+                                           cudaStream_t st);  // rc_inst.cu
+
+template <typename S>
+static cudaError_t launch_k3(const LevelCfg &c, const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
+  if constexpr (sizeof(S) == 8) {
+    if (c.rc_mout > 0) return launch_recompose_dmma_dispatch(p, n_items, c.rc_mout, c.rc_k, c.rc_ncl, st);
+  }
+  return launch_side_kernel<S>(true, c, p, n_items, st);
+}
 
 template <typename S>
 static cudaError_t launch_k2(const LevelCfg &c, const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
@@ -444,7 +467,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     if (e->profile) cudaEventRecord(e->pev[1], e->stream);
     if (st == cudaSuccess) st = launch_k2<S>(c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[2], e->stream);
-    if (st == cudaSuccess) st = launch_side_kernel<S>(true, c, p, n_items, e->stream);
+    if (st == cudaSuccess) st = launch_k3<S>(c, p, n_items, e->stream);
     if (e->profile) {
       cudaEventRecord(e->pev[3], e->stream);
       cudaEventSynchronize(e->pev[3]);
@@ -781,6 +804,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
     env = getenv("TNSU_SVD_V");
     e->svd_accumulate_v = env && std::string(env) == "accumulate";
+    env = getenv("TNSU_RC");
+    e->force_simple_rc = env && std::string(env) == "simple";
     env = getenv("TNSU_RDM");
     e->force_simple_rdm = env && std::string(env) == "simple";
   }

@@ -172,13 +172,14 @@ def test_unsupported_shapes_fail_loudly(tnsu):
 
 def test_svd_kernels_agree(tnsu, monkeypatch):
     """The register-resident warp SVD (V-free with recovered right vectors = the default, with accumulated V, without
-    the pivoted-QR preconditioner) and the shared-memory Jacobi kernel are interchangeable: same weights and energy
-    on the BASELINE config-2 shape."""
+    the pivoted-QR preconditioner) and the shared-memory Jacobi kernel are interchangeable, and so are the tensor-core
+    and the register-column K3: same weights and energy on the BASELINE config-2 shape."""
     smat = tnsu.smc.infinite_structure_matrix_dict("peps")
     sx, sy, sz = tnsu.spin_operators(0.5)
     results = []
-    for env in ({}, {"TNSU_SVD_V": "accumulate"}, {"TNSU_SVD_PRECOND": "0"}, {"TNSU_SVD": "smem"}, {"TNSU_LQ": "unrolled"}):
-        for k in ("TNSU_SVD_PRECOND", "TNSU_SVD", "TNSU_LQ", "TNSU_SVD_V"):
+    for env in ({}, {"TNSU_SVD_V": "accumulate"}, {"TNSU_SVD_PRECOND": "0"}, {"TNSU_SVD": "smem"}, {"TNSU_LQ": "unrolled"},
+                {"TNSU_RC": "simple"}):
+        for k in ("TNSU_SVD_PRECOND", "TNSU_SVD", "TNSU_LQ", "TNSU_SVD_V", "TNSU_RC"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
