@@ -434,13 +434,13 @@ def run_gpu_arm(args):
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
-                         "kernel": "edge update = lq_rolled_kernel + svd_warp_kernel + recompose_kernel (one level)",
+                         "kernel": "edge update = lq_rolled_kernel + svd_warp_kernel + recompose_dmma_kernel (one level)",
                          "launches": int(n_triples), "algorithmic_bytes_per_launch": alg_launch,
                          "avg_launch_ms": kern_ms / n_triples,
                          "ncu": {k: ncu.get(k) for k in ("kernel_time_us", "fp64_pipe_pct", "dram_throughput_pct", "source")},
                          "fp64_peak_tflops_measured": 36.2,
                          "note": "the edge update is FP64-pipe / latency bound, not HBM bound (DESIGN.md section 4): the SVD "
-                                 "kernel moves almost no bytes and runs the FP64 pipe at ~41 %; traffic is 2x the algorithmic "
+                                 "kernel moves almost no bytes and runs the FP64 pipe at ~39 %; traffic is 2x the algorithmic "
                                  "bytes because the Householder reflectors travel through HBM between K1 and K3"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cpu_edges} edge updates of one peps D=8 network, numpy/scipy oracle, 1 BLAS thread"},
@@ -463,6 +463,8 @@ def run_gpu_arm(args):
                          "reference_shaped_bytes_per_launch": en_ref,
                          "reference_shaped_gbs": en_ref / (energy_ms * 1e-3) / 1e9,
                          "kernel": "pair_rdm_dmma_kernel<2> (+ pair_sum_kernel, 71 KB D2H)" if not cplx else "pair_rdm_kernel<cplx>",
+                         "traffic": None if (cplx or "pair_rdm_dram_bytes_per_evaluation" not in ncu) else
+                         ncu["pair_rdm_dram_bytes_per_evaluation"] * batch,
                          "dmma_tflops": None if cplx else dmma_flop / (energy_ms * 1e-3) / 1e12,
                          "dmma_peak_tflops_measured": 37.0},
         }
