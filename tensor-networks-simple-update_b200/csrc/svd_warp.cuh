@@ -203,27 +203,31 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
   if (valid) {
     for (int idx = gl; idx < Ki * Kj; idx += G) {
       const int qi = idx / Kj, qj = idx - qi * Kj;
-      double x[TNSU_MAX_SPIN][TNSU_MAX_SPIN];
+      // rolled over (i, j): straight-line code here would only evict the Jacobi loop of the other warps from the
+      // instruction cache
+      double out[TNSU_MAX_SPIN][TNSU_MAX_SPIN];
 #pragma unroll
-      for (int i = 0; i < TNSU_MAX_SPIN; ++i)
+      for (int ip = 0; ip < TNSU_MAX_SPIN; ++ip)
 #pragma unroll
-        for (int j = 0; j < TNSU_MAX_SPIN; ++j) {
-          double a = 0.0;
-          if (i < d && j < d)
-            for (int e = 0; e < Dk; ++e) a = fma(Li[(i * Dk + e) * ldm + qi] * lam_old[e], Lj[(j * Dk + e) * ldm + qj], a);
-          x[i][j] = a;
-        }
+        for (int jp = 0; jp < TNSU_MAX_SPIN; ++jp) out[ip][jp] = 0.0;
+#pragma unroll 1
+      for (int ij = 0; ij < d * d; ++ij) {
+        const int i = ij / d, j = ij - i * d;
+        double a = 0.0;
+        for (int e = 0; e < Dk; ++e) a = fma(Li[(i * Dk + e) * ldm + qi] * lam_old[e], Lj[(j * Dk + e) * ldm + qj], a);
+        const double *gp = gate_s + ij * d * d;
+#pragma unroll
+        for (int ip = 0; ip < TNSU_MAX_SPIN; ++ip)
+#pragma unroll
+          for (int jp = 0; jp < TNSU_MAX_SPIN; ++jp)
+            if (ip < d && jp < d) out[ip][jp] = fma(a, gp[ip * d + jp], out[ip][jp]);
+      }
 #pragma unroll
       for (int ip = 0; ip < TNSU_MAX_SPIN; ++ip)
 #pragma unroll
         for (int jp = 0; jp < TNSU_MAX_SPIN; ++jp) {
           if (ip < d && jp < d) {
-            double a = 0.0;
-#pragma unroll
-            for (int i = 0; i < TNSU_MAX_SPIN; ++i)
-#pragma unroll
-              for (int j = 0; j < TNSU_MAX_SPIN; ++j)
-                if (i < d && j < d) a = fma(x[i][j], gate_s[((i * d + j) * d + ip) * d + jp], a);
+            const double a = out[ip][jp];
             const int row = qi * d + ip, cl = jp * Kj + qj;
             if (transposed)
               th[(size_t)row * lda + cl] = a;  // A = theta^T
@@ -554,33 +558,45 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
     const double *thh = th + (size_t)(h * R) * lda;
     double *rt_i = valid ? small + SM_R0 * ldm * ldm : nullptr;
     const int n_rowidx = valid ? p.descs[ek].ni : 0;
-#pragma unroll
+    // theta-row index (qi, i') of my first row, advanced without divisions
+    const int gr0 = h * R;
+    const int qi0 = gr0 / d, ip0 = gr0 - qi0 * d;
+#pragma unroll 1
     for (int which = 0; which < 2; ++which) {
-      double(&ua)[R] = which ? ya : xa;
-      double(&w)[R] = which ? wy : wx;
+      // the loop body always works on (xa -> wx); the second trip sees the y column through a register swap
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int c = 0; c < R; ++c) {
-          s0 = fma(thh[(size_t)c * lda + r], ua[c], s0);
-          s1 = fma(thh[(size_t)c * lda + R + r], ua[c], s1);
+          s0 = fma(thh[(size_t)c * lda + r], xa[c], s0);
+          s1 = fma(thh[(size_t)c * lda + R + r], xa[c], s1);
         }
         const double mine = h ? s1 : s0, other = h ? s0 : s1;
-        w[r] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+        wx[r] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
       }
       if (which ? sel_y : sel_x) {
         const int xp = which ? rank_y : rank_x;
+        int qi = qi0, ip = ip0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int gr = h * R + r;
-          if (gr < n_rowidx) {
-            const int qi = gr / d, ip = gr - qi * d;
-            rt_i[(ip * Dnew + xp) * ldm + qi] = ua[r];
+          if (gr0 + r < n_rowidx) rt_i[(ip * Dnew + xp) * ldm + qi] = xa[r];
+          if (++ip == d) {
+            ip = 0;
+            ++qi;
           }
         }
       }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double ta = xa[r], tw = wx[r];
+        xa[r] = ya[r];
+        ya[r] = ta;
+        wx[r] = wy[r];
+        wy[r] = tw;
+      }
     }
+    // after two swaps xa / ya are back in place and (wx, wy) hold the vectors of (x, y)
     // a kept column with no direction of its own (sigma = 0, or theta^T u underflows) starts from a fixed dense vector
     {
       double n2x = 0.0, n2y = 0.0;
@@ -592,6 +608,7 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
       n2x += __shfl_xor_sync(0xffffffffu, n2x, 1);
       n2y += __shfl_xor_sync(0xffffffffu, n2y, 1);
       const bool fx = sel_x && !(n2x > 1e-280), fy = sel_y && !(n2y > 1e-280);
+      if (__any_sync(0xffffffffu, fx || fy))  // rare: keep it out of the instruction stream otherwise
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int c = h * R + r;
@@ -646,12 +663,13 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
         const bool sel = which ? sel_y : sel_x;
         const int xp = which ? rank_y : rank_x;
         if (sel) {
+          int jp = (h * R) / Kj, qj = h * R - jp * Kj;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const int gr = h * R + r;
-            if (gr < n_colidx) {
-              const int jp = gr / Kj, qj = gr - jp * Kj;
-              rt_j[(jp * Dnew + xp) * ldm + qj] = which ? wy[r] : wx[r];
+            if (h * R + r < n_colidx) rt_j[(jp * Dnew + xp) * ldm + qj] = which ? wy[r] : wx[r];
+            if (++qj == Kj) {
+              qj = 0;
+              ++jp;
             }
           }
         }
