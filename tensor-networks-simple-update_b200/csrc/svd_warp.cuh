@@ -77,25 +77,30 @@ DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (
   return rot;
 }
 
-// the same step on the A columns alone (svd_warp_kernel<R, false>: the right vectors are recovered afterwards)
+// One step of the odd-even ordering in a form that serves BOTH half steps with the same code (the Jacobi loop body
+// then is a single copy of ~300 instructions instead of two): with flip = false it is svdw_rotate on the pair
+// (x, y) without the V rows, outputs swapped; with flip = true it is the same on (y, x), written in terms of (x, y):
+//   flip = false:  x' = s x + c y,  y' = c x - s y        flip = true:  x' = -s x + c y,  y' = c x + s y
+// where (c, s) come from (al, be, ga) = (|P|^2, |Q|^2, P.Q) of the ordered pair (P, Q) = flip ? (y, x) : (x, y).
 template <int R>
-DEV bool svdw_rotate_a(double (&pa)[R], double (&qa)[R], bool idle) {
-  double al0 = 0.0, al1 = 0.0, be0 = 0.0, be1 = 0.0, ga0 = 0.0, ga1 = 0.0;
+DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
+  double nx0 = 0.0, nx1 = 0.0, ny0 = 0.0, ny1 = 0.0, ga0 = 0.0, ga1 = 0.0;
 #pragma unroll
   for (int r = 0; r < R; r += 2) {
-    al0 = fma(pa[r], pa[r], al0);
-    be0 = fma(qa[r], qa[r], be0);
-    ga0 = fma(pa[r], qa[r], ga0);
+    nx0 = fma(xa[r], xa[r], nx0);
+    ny0 = fma(ya[r], ya[r], ny0);
+    ga0 = fma(xa[r], ya[r], ga0);
     if (r + 1 < R) {
-      al1 = fma(pa[r + 1], pa[r + 1], al1);
-      be1 = fma(qa[r + 1], qa[r + 1], be1);
-      ga1 = fma(pa[r + 1], qa[r + 1], ga1);
+      nx1 = fma(xa[r + 1], xa[r + 1], nx1);
+      ny1 = fma(ya[r + 1], ya[r + 1], ny1);
+      ga1 = fma(xa[r + 1], ya[r + 1], ga1);
     }
   }
-  double al = al0 + al1, be = be0 + be1, ga = ga0 + ga1;
-  al += __shfl_xor_sync(0xffffffffu, al, 1);
-  be += __shfl_xor_sync(0xffffffffu, be, 1);
+  double nx = nx0 + nx1, ny = ny0 + ny1, ga = ga0 + ga1;
+  nx += __shfl_xor_sync(0xffffffffu, nx, 1);
+  ny += __shfl_xor_sync(0xffffffffu, ny, 1);
   ga += __shfl_xor_sync(0xffffffffu, ga, 1);
+  const double al = flip ? ny : nx, be = flip ? nx : ny;
   const double tol2 = 2.25e-30;
   const double g2 = ga * ga;
   const bool rot = !idle && (g2 > tol2 * al * be) && (g2 > 0.0);
@@ -112,11 +117,12 @@ DEV bool svdw_rotate_a(double (&pa)[R], double (&qa)[R], bool idle) {
     c = 0.0;
     s = 1.0;
   }
+  const double sa = flip ? -s : s;  // x' = sa x + c y,  y' = c x - sa y
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const double p0 = pa[r], q0 = qa[r];
-    pa[r] = fma(s, p0, c * q0);
-    qa[r] = fma(c, p0, -(s * q0));
+    const double x0 = xa[r], y0 = ya[r];
+    xa[r] = fma(sa, x0, c * y0);
+    ya[r] = fma(c, x0, -(sa * y0));
   }
   return rot;
 }
@@ -445,35 +451,49 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
 
   const long long clk_b = clock64();
   int sweeps = 0;
-  for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
-    bool rotated = false;
-    for (int st = 0; st < NP; ++st) {
-      // step A: pairs (x_k, y_k)
-      if constexpr (ACCV)
+  if constexpr (ACCV) {
+    for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
+      bool rotated = false;
+      for (int st = 0; st < NP; ++st) {
+        // step A: pairs (x_k, y_k)
         rotated |= svdw_rotate<R>(xa, xv, ya, yv, false);
-      else
-        rotated |= svdw_rotate_a<R>(xa, ya, false);
-      // layout A -> B: x_k <- x_{k+1}  (the last processor receives position 0)
+        // layout A -> B: x_k <- x_{k+1}  (the last processor receives position 0)
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        xa[r] = __shfl_sync(0xffffffffu, xa[r], src_next);
-        if constexpr (ACCV) xv[r] = __shfl_sync(0xffffffffu, xv[r], src_next);
-      }
-      // step B: pairs (y_k, x_k) = positions (2k+1, 2k+2); the last processor idles
-      if constexpr (ACCV)
+        for (int r = 0; r < R; ++r) {
+          xa[r] = __shfl_sync(0xffffffffu, xa[r], src_next);
+          xv[r] = __shfl_sync(0xffffffffu, xv[r], src_next);
+        }
+        // step B: pairs (y_k, x_k) = positions (2k+1, 2k+2); the last processor idles
         rotated |= svdw_rotate<R>(ya, yv, xa, xv, last);
-      else
-        rotated |= svdw_rotate_a<R>(ya, xa, last);
-      // layout B -> A
+        // layout B -> A
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        xa[r] = __shfl_sync(0xffffffffu, xa[r], src_prev);
-        if constexpr (ACCV) xv[r] = __shfl_sync(0xffffffffu, xv[r], src_prev);
+        for (int r = 0; r < R; ++r) {
+          xa[r] = __shfl_sync(0xffffffffu, xa[r], src_prev);
+          xv[r] = __shfl_sync(0xffffffffu, xv[r], src_prev);
+        }
+      }
+      if (!__any_sync(0xffffffffu, rotated)) {
+        ++sweeps;
+        break;
       }
     }
-    if (!__any_sync(0xffffffffu, rotated)) {
-      ++sweeps;
-      break;
+  } else {
+    // one half step per trip (step A: pair (x_k, y_k), then x_k <- x_{k+1}; step B: pair (y_k, x_k), the last
+    // processor idle, then x_k <- x_{k-1}): a single copy of the step in the instruction stream
+    for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
+      bool rotated = false;
+#pragma unroll 1
+      for (int st = 0; st < 2 * NP; ++st) {
+        const bool flip = (st & 1) != 0;
+        rotated |= svdw_step_a<R>(xa, ya, flip, flip && last);
+        const int src = flip ? src_prev : src_next;
+#pragma unroll
+        for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src);
+      }
+      if (!__any_sync(0xffffffffu, rotated)) {
+        ++sweeps;
+        break;
+      }
     }
   }
 
@@ -556,6 +576,8 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
     // (one column at a time, its r~_i written right away, so that A and W never sit in registers together)
     double wx[R], wy[R];
     const double *thh = th + (size_t)(h * R) * lda;
+    double *wt = gs + p.svdw_tb_off;  // R x ldt, free since the transposition
+    const int ldt_w = p.svdw_ldt;
     double *rt_i = valid ? small + SM_R0 * ldm * ldm : nullptr;
     const int n_rowidx = valid ? p.descs[ek].ni : 0;
     // theta-row index (qi, i') of my first row, advanced without divisions
@@ -564,17 +586,28 @@ __global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) 
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       // the loop body always works on (xa -> wx); the second trip sees the y column through a register swap
-#pragma unroll
+      // rolled over the output row (results pass through the dead transpose buffer): R x 2R FMAs of straight-line
+      // code per column would be a quarter of the kernel's instructions
+#pragma unroll 1
       for (int r = 0; r < R; ++r) {
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int c = 0; c < R; ++c) {
+        for (int c = 0; c < R; c += 2) {
           s0 = fma(thh[(size_t)c * lda + r], xa[c], s0);
           s1 = fma(thh[(size_t)c * lda + R + r], xa[c], s1);
+          s2 = fma(thh[(size_t)(c + 1) * lda + r], xa[c + 1], s2);
+          s3 = fma(thh[(size_t)(c + 1) * lda + R + r], xa[c + 1], s3);
         }
+        s0 += s2;
+        s1 += s3;
         const double mine = h ? s1 : s0, other = h ? s0 : s1;
-        wx[r] = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+        const double tot = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+        if (in_group) wt[(size_t)r * ldt_w + gl] = tot;
       }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < R; ++r) wx[r] = wt[(size_t)r * ldt_w + (in_group ? gl : 0)];
+      __syncwarp();
       if (which ? sel_y : sel_x) {
         const int xp = which ? rank_y : rank_x;
         int qi = qi0, ip = ip0;
