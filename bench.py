@@ -496,10 +496,19 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    # exactly ONE line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its version
+    # there) are sent to stderr for the duration of the run; the JSON line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_gpu_arm(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
