@@ -518,6 +518,7 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
   PairRdmLaunch<S> p{};
   p.descs = e->d_descs;
   p.edge_list = edge_list;
+  p.first_edge = (edge_list >= e->d_all_edges && edge_list < e->d_all_edges + e->m) ? (int)(edge_list - e->d_all_edges) : -1;
   p.n_list = n_list;
   p.batch = e->batch;
   p.m_edges = e->m;

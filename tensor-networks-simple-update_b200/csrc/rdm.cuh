@@ -20,6 +20,7 @@ template <typename S>
 struct PairRdmLaunch {
   const EdgeDesc *descs;
   const int *edge_list;  // edges handled by this launch
+  int first_edge;        // >= 0: the list is first_edge, first_edge + 1, ... (saves a dependent global load per CTA)
   int n_list;
   int batch, m_edges, dcap, d4;
   const double *weights;
@@ -203,6 +204,16 @@ DEV void dmma884(double &c0, double &c1, double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// 16- / 32-byte read-only global loads (LDG.E.128 / LDG.E.256 on sm_100a); the address must be aligned to the width
+template <int W>
+DEV void pg_ldvec(const char *ptr, double (&v)[W]) {
+  static_assert(W == 2 || W == 4, "vector width");
+  if constexpr (W == 2)
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(ptr));
+  else
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(ptr));
+}
+
 struct __align__(16) PgCol {  // one column of the bond matrix: squared environment weight and element offset
   double w;
   int off;
@@ -226,7 +237,8 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   constexpr int MP = 8 * MB;
   constexpr int NBLK = MB * (MB + 1) / 2;
   const int b = blockIdx.x / p.n_list;
-  const int ek = p.edge_list[blockIdx.x - b * p.n_list];
+  const int ek = p.first_edge >= 0 ? p.first_edge + (int)(blockIdx.x - b * p.n_list) : p.edge_list[blockIdx.x - b * p.n_list];
+  const int ek_first = p.first_edge >= 0 ? p.first_edge : p.edge_list[0];
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.iter_state != nullptr) {
     const int it = p.iter_state[b];
@@ -278,10 +290,30 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
       asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + o));
   }
   // rows past M are clamped to row 0: their Gram entries are computed and never read
+  // How the fragments are fetched (warp-uniform, per side).  The LSU wavefront rate, not DRAM, bounded the first
+  // version (8 lines touched per 8-byte-per-lane load), so wherever the layout allows it one lane fetches 32 bytes:
+  //   mode 1  the innermost tensor axis is an environment leg (dim % 4 == 0): a lane takes FOUR consecutive columns of
+  //           its row with one LDG.256 and feeds four k-steps from it.  Within a 16-column group k-step j then holds
+  //           the columns 4t + j instead of 4j + t — a permutation of the summation index, the same for A and B.
+  //   mode 2  the bond leg is the innermost axis: the rows (s, x_k .. x_k + MB - 1) are contiguous, so fragment row g of
+  //           block I is bond-matrix row g * MB + I and ONE 16/32-byte load serves all MB row blocks of a k-step.
+  //   mode 0  everything else (odd dimensions, unaligned slices): one 8-byte load per row block and k-step.
+  int mode = 0;
+  {
+    const bool inner_bond = sd.bond_leg == sd.nlegs - 1;
+    const int lin = sd.nlegs - 1 - (inner_bond ? 1 : 0);  // innermost environment leg
+    const bool aligned = (((size_t)sd.base & 31) == 0) && (sd.point_stride % 4 == 0) && (sd.in_stride_phys % 4 == 0);
+    if (!inner_bond) {
+      if (aligned && lin >= 0 && sd.dims[lin] % 4 == 0 && sd.in_stride[lin] == 1 && sd.in_stride[sd.bond_leg] % 4 == 0) mode = 1;
+    } else if ((MB == 2 || MB == 4) && sd.nlegs >= 2) {
+      if (aligned && sd.in_stride[sd.bond_leg] == 1 && Dk % MB == 0 && (Dk % 4 == 0 || MB == 2)) mode = 2;
+    }
+  }
   const char *rowp[MB];
 #pragma unroll
   for (int I = 0; I < MB; ++I) {
-    const int r = 8 * I + g < M ? 8 * I + g : 0;
+    const int rr = (mode == 2) ? g * MB + I : 8 * I + g;
+    const int r = rr < M ? rr : 0;
     const int s = r / Dk, x = r - s * Dk;
     rowp[I] = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride + (long long)s * sd.in_stride_phys +
                              (long long)x * sd.in_stride[sd.bond_leg]);
@@ -296,40 +328,123 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   constexpr int KSTEP_GROUP = 4 * PG_UNROLL;  // k-steps per trip of the four warps of a side
   for (int c0 = 0; c0 < Nmax; c0 += PG_CHUNK) {
     __syncthreads();  // legs / wsq ready, previous chunk consumed
-    for (int idx = tid; idx < 2 * PG_CHUNK; idx += PG_THREADS) {
+    // each thread decodes 2 * PG_CHUNK / PG_THREADS entries, unrolled: the weight products are dependent FP64 chains
+#pragma unroll
+    for (int it = 0; it < 2 * PG_CHUNK / PG_THREADS; ++it) {
+      const int idx = tid + it * PG_THREADS;
       const int sdx = idx / PG_CHUNK, cc = idx - sdx * PG_CHUNK;  // uniform per warp
       const int Ns = sdx ? N1 : N0;
       const int left = Ns - c0;
-      if (left <= 0) continue;
-      const int nks_pad = (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP;
-      if (cc >= 4 * nks_pad) continue;
-      PgCol e;
-      e.w = 0.0;
-      e.off = 0;
-      e.pad = 0;
-      if (cc < left) {
-        const PgLeg *lg = legs + sdx * TNSU_MAX_LEGS;
-        const double *wl = wsq + sdx * TNSU_MAX_LEGS * PG_WL;
-        const int nenv = sdx ? nenv1 : nenv0;
-        unsigned rem = (unsigned)(c0 + cc);
-        double w = 1.0;
-        unsigned off = 0;
-        for (int k = 0; k < nenv; ++k) {
-          const PgLeg L = lg[k];
-          const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
-          const unsigned x = rem - qq * (unsigned)L.dim;
-          rem = qq;
-          off += x * (unsigned)L.stride;
-          w *= wl[k * PG_WL + x];
+      const int nks_pad = left > 0 ? (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP : 0;
+      if (cc < 4 * nks_pad) {
+        PgCol e;
+        e.w = 0.0;
+        e.off = 0;
+        e.pad = 0;
+        if (cc < left) {
+          const PgLeg *lg = legs + sdx * TNSU_MAX_LEGS;
+          const double *wl = wsq + sdx * TNSU_MAX_LEGS * PG_WL;
+          const int nenv = sdx ? nenv1 : nenv0;
+          unsigned rem = (unsigned)(c0 + cc);
+          double w = 1.0;
+          unsigned off = 0;
+          for (int k = 0; k < nenv; ++k) {
+            const PgLeg L = lg[k];
+            const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
+            const unsigned x = rem - qq * (unsigned)L.dim;
+            rem = qq;
+            off += x * (unsigned)L.stride;
+            w *= wl[k * PG_WL + x];
+          }
+          e.w = w;
+          e.off = (int)(off * 8u);  // byte offset
         }
-        e.w = w;
-        e.off = (int)(off * 8u);  // byte offset
+        cols[idx] = e;
       }
-      cols[idx] = e;
     }
     __syncthreads();
     const int left = sd.N - c0;
-    if (left > 0) {
+    if (left > 0 && mode == 1) {
+      // groups of 16 columns; this warp takes groups q, q + 4, ...; the next group's loads fly during the DMMAs
+      const int ngr = ((((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP) >> 2;
+      const PgCol *cg = cols + side * PG_CHUNK + 4 * t;
+      double v[MB][4], w[4];
+      {
+        const PgCol *e = cg + 16 * q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = e[j].w;
+        const unsigned off = (unsigned)e[0].off;
+#pragma unroll
+        for (int I = 0; I < MB; ++I) pg_ldvec<4>(rowp[I] + off, v[I]);
+      }
+#pragma unroll 1
+      for (int gr = q; gr < ngr; gr += 4) {
+        double vn[MB][4], wn[4];
+        {
+          const PgCol *e = cg + 16 * (gr + 4 < ngr ? gr + 4 : gr);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wn[j] = e[j].w;
+          const unsigned off = (unsigned)e[0].off;
+#pragma unroll
+          for (int I = 0; I < MB; ++I) pg_ldvec<4>(rowp[I] + off, vn[I]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int k = 0;
+#pragma unroll
+          for (int I = 0; I < MB; ++I) {
+            const double a = v[I][j] * w[j];
+#pragma unroll
+            for (int J = 0; J <= I; ++J, ++k) dmma884(acc[k][0], acc[k][1], a, v[J][j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[j] = wn[j];
+#pragma unroll
+          for (int I = 0; I < MB; ++I) v[I][j] = vn[I][j];
+        }
+      }
+    } else if (left > 0 && mode == 2) {
+      if constexpr (MB == 2 || MB == 4) {
+        const int nks_pad = (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP;
+        const PgCol *cl = cols + side * PG_CHUNK + t;
+        double v[PG_UNROLL][MB], w[PG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PG_UNROLL; ++u) {
+          const PgCol e = cl[4 * (q + 4 * u)];
+          w[u] = e.w;
+          pg_ldvec<MB>(rowp[0] + (unsigned)e.off, v[u]);
+        }
+#pragma unroll 1
+        for (int ks0 = q; ks0 < nks_pad; ks0 += KSTEP_GROUP) {
+          double vn[PG_UNROLL][MB], wn[PG_UNROLL];
+          const int ksn = ks0 + KSTEP_GROUP < nks_pad ? ks0 + KSTEP_GROUP : ks0;
+#pragma unroll
+          for (int u = 0; u < PG_UNROLL; ++u) {
+            const PgCol e = cl[4 * (ksn + 4 * u)];
+            wn[u] = e.w;
+            pg_ldvec<MB>(rowp[0] + (unsigned)e.off, vn[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < PG_UNROLL; ++u) {
+            int k = 0;
+#pragma unroll
+            for (int I = 0; I < MB; ++I) {
+              const double a = v[u][I] * w[u];
+#pragma unroll
+              for (int J = 0; J <= I; ++J, ++k) dmma884(acc[k][0], acc[k][1], a, v[u][J]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PG_UNROLL; ++u) {
+            w[u] = wn[u];
+#pragma unroll
+            for (int I = 0; I < MB; ++I) v[u][I] = vn[u][I];
+          }
+        }
+      }
+    } else if (left > 0) {
       const int nks_pad = (((min(left, PG_CHUNK) + 3) >> 2) + KSTEP_GROUP - 1) / KSTEP_GROUP * KSTEP_GROUP;
       const PgCol *cl = cols + side * PG_CHUNK + t;
       // software pipeline: the loads of trip n+1 are in flight while the DMMAs of trip n issue
@@ -372,6 +487,8 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
     }
   }
   // sum the four partial fragments of each side in warp order; tile (I,J) element [g][2t+{0,1}]
+  int *modes = (int *)(red + 1);  // [2] fetch mode of each side (for the symmetric fill below)
+  if (lane == 0 && q == 0) modes[side] = mode;
   double *gs = gram + side * MP * MP;
   for (int wv = 0; wv < 4; ++wv) {
     __syncthreads();
@@ -381,12 +498,18 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
       for (int I = 0; I < MB; ++I)
 #pragma unroll
         for (int J = 0; J <= I; ++J, ++k) {
-          double2 *dst = (double2 *)(gs + (8 * I + g) * MP + 8 * J + 2 * t);
-          double2 cur = make_double2(0.0, 0.0);
-          if (wv != 0) cur = *dst;
-          cur.x += acc[k][0];
-          cur.y += acc[k][1];
-          *dst = cur;
+          // fragment (block I, row g) is bond-matrix row 8 I + g, or g MB + I in mode 2; same for the columns
+          const int r = (mode == 2) ? g * MB + I : 8 * I + g;
+          const int ca = (mode == 2) ? (2 * t) * MB + J : 8 * J + 2 * t;
+          const int cb = (mode == 2) ? (2 * t + 1) * MB + J : 8 * J + 2 * t + 1;
+          double *da = gs + r * MP + ca, *db = gs + r * MP + cb;
+          double xa = 0.0, xb = 0.0;
+          if (wv != 0) {
+            xa = *da;
+            xb = *db;
+          }
+          *da = xa + acc[k][0];
+          *db = xb + acc[k][1];
         }
     }
   }
@@ -395,11 +518,13 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   for (int idx = tid; idx < 2 * MP * MP; idx += PG_THREADS) {
     const int sdx = idx / (MP * MP), rest = idx - sdx * MP * MP;
     const int r = rest / MP, c = rest - r * MP;
-    if ((r >> 3) >= (c >> 3)) {
+    const bool m2 = modes[sdx] == 2;
+    const int br = m2 ? r % MB : r >> 3, bc = m2 ? c % MB : c >> 3;  // row-block ids: only blocks I >= J were computed
+    if (br >= bc) {
       double v = gram[idx];
       if (sdx) v *= lamrow[r] * lamrow[c];
       gram[idx] = v;
-      if ((r >> 3) > (c >> 3)) gram[sdx * MP * MP + c * MP + r] = v;
+      if (br > bc) gram[sdx * MP * MP + c * MP + r] = v;
     }
   }
   __syncthreads();
@@ -434,7 +559,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   }
   __syncthreads();
   const double itr = red[0];
-  if (p.rdm_out != nullptr && ek == p.edge_list[0])
+  if (p.rdm_out != nullptr && ek == ek_first)
     for (int idx = tid; idx < p.d4; idx += PG_THREADS) p.rdm_out[(size_t)b * p.d4 + idx] = mkc(rho[idx] * itr, 0.0);
   if (p.pair_val != nullptr && warp == 0) {
     const double *op = p.ops + (size_t)b * p.op_point_stride + (size_t)ek * p.op_edge_stride;
