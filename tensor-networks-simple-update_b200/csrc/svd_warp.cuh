@@ -136,7 +136,7 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
 // and on product states with weights down to 1e-16 with a numpy model of this route before it was written);
 // vectors of (numerically) zero singular values become an arbitrary orthonormal completion, as they are in LAPACK.
 template <int R, bool ACCV>
-__global__ void __launch_bounds__(SVDW_THREADS, ACCV ? ((R > 12) ? 3 : ((R > 6) ? 4 : 6)) : ((R > 8) ? 4 : 6))
+__global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? ((R > 12) ? 3 : ((R > 6) ? 4 : 6)) : ((R > 8) ? 4 : 6)))
     svd_warp_kernel(const EdgeLaunch<double> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
