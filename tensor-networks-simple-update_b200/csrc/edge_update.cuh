@@ -78,6 +78,7 @@ struct EdgeLaunch {
   int svdw_group_doubles;    // shared-memory doubles per theta in svd_warp_kernel
   int svdw_precond;          // pivoted-QR preconditioner before the Jacobi iteration
   int svdw_ldt;              // leading dimension of its transpose buffer
+  const int *lq_flags;       // streaming K1/K3 (lq_chol.cuh) ran first: per (item, side) 1 = the Householder kernels must process it, 0 = skip; nullptr = process all
   int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;
@@ -492,6 +493,8 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
       return;
     }
   }
+
+  if (p.lq_flags != nullptr && p.lq_flags[w] == 0) return;  // factored by the streaming CholeskyQR2 kernel already
 
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];

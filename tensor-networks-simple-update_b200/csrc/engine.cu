@@ -27,6 +27,7 @@ struct LevelCfg {
   int lda = 0, ldv = 0, nr_max = 0;
   int smem_lq = 0, smem_svd = 0, smem_rc = 0;
   int svdw_precond = 0, svdw_ldt = 0, svdw_accv = 1, svdw_tb_off = 0;
+  int lqc = 0, lqc_m = 0;  // streaming CholeskyQR2 K1/K3 (lq_chol.cuh) in front of the Householder kernels; largest M of the level
   int rc_mout = 0, rc_k = 0, rc_ncl = 0;  // tensor-core K3 (recompose_dmma.cuh): largest Mout, K and slice width; 0 = not used
   int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
   int cluster = 1;                                                   // CTAs per (item, side) in K1 / K3
@@ -80,6 +81,8 @@ struct tnsu_engine {
   bool use_graphs = false;                // TNSU_GRAPH=1: replay the run-loop iteration as a CUDA graph (measured: no faster)
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
+  bool force_householder = false;         // TNSU_LQ=householder: no streaming CholeskyQR2 K1/K3 in front of the Householder kernels (A/B comparisons)
+  int *lq_flags = nullptr;                // [batch * max_level_size * 2] per (item, side): 1 = Householder kernels must process it
   bool force_simple_rc = false;           // TNSU_RC=simple: register-column K3 (recompose_kernel) instead of the tensor-core one (A/B comparisons)
   bool force_simple_rdm = false;          // TNSU_RDM=simple: shared-memory-staged pair RDM kernel instead of the DMMA one (A/B comparisons)
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
@@ -310,6 +313,30 @@ static int plan_sweep(tnsu_engine *e) {
       }
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
+    if (!cx && !e->force_householder && !e->force_simple_rc && !e->lq_stream && !e->force_unrolled_lq && e->dcap <= 32 &&
+        c.cluster == 1) {
+      // streaming K1/K3: every side of the level must have M <= N, an unchanged bond dimension (the recompose runs in
+      // place) and tensors below 2 GiB (32-bit byte offsets)
+      bool ok_lqc = true;
+      int mm = 1;
+      for (int ek : e->level_edges[lv]) {
+        const EdgeDesc &ed = e->h_descs[ek];
+        if (ed.Dnew != ed.Dk) ok_lqc = false;
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const SideDesc &sd2 = ed.s[s2];
+          if (sd2.M > sd2.N || sd2.Mout != sd2.M) ok_lqc = false;
+          if ((long long)sd2.M * sd2.N * 8 >= (1LL << 31)) ok_lqc = false;
+          for (int l = 0; l < sd2.nlegs; ++l)
+            if (sd2.in_stride[l] != sd2.out_stride[l]) ok_lqc = false;
+          if (sd2.in_stride_phys != sd2.out_stride_phys) ok_lqc = false;
+          mm = std::max(mm, sd2.M);
+        }
+      }
+      if (ok_lqc) {
+        c.lqc = 1;
+        c.lqc_m = mm;
+      }
+    }
     if (!cx && !e->force_simple_rc && e->dcap <= 32) {
       int mo = 1, kk = 1;
       for (int ek : e->level_edges[lv])
@@ -334,6 +361,10 @@ static int plan_sweep(tnsu_engine *e) {
       cudaError_t st2 = cudaMalloc(&e->small, need);
       if (st2 != cudaSuccess) return fail(e, TNSU_E_CUDA, "scratch allocation of %zu bytes: %s", need, cudaGetErrorString(st2));
       e->small_bytes = need;
+    }
+    if (e->lq_flags == nullptr) {
+      cudaError_t st3 = cudaMalloc(&e->lq_flags, sizeof(int) * 2 * (size_t)e->batch * e->max_level_size);
+      if (st3 != cudaSuccess) return fail(e, TNSU_E_CUDA, "flag allocation: %s", cudaGetErrorString(st3));
     }
   }
   cudaError_t st = cudaMemcpyAsync(e->d_descs, e->h_descs.data(), sizeof(EdgeDesc) * e->m, cudaMemcpyHostToDevice,
@@ -385,6 +416,8 @@ static cudaError_t launch_side_kernel(bool recompose, const LevelCfg &c, const E
 }
 
 cudaError_t launch_svd_warp_dispatch(const EdgeLaunch<double> &p, int n_items, cudaStream_t st);  // svdw_inst.cu
+cudaError_t launch_lq_chol_dispatch(const EdgeLaunch<double> &p, int n_items, int m_max, int *flags, cudaStream_t st);  // lqc_inst.cu
+cudaError_t launch_rc_chol_dispatch(const EdgeLaunch<double> &p, int n_items, int m_max, const int *flags, cudaStream_t st);
 cudaError_t launch_recompose_dmma_dispatch(const EdgeLaunch<double> &p, int n_items, int mout_max, int k_max, int ncl_cap,
                                            cudaStream_t st);  // rc_inst.cu
 
@@ -452,6 +485,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_group_doubles = c.svdw_group_doubles;
     p.svdw_precond = c.svdw_precond;
     p.svdw_ldt = c.svdw_ldt;
+    p.lq_flags = nullptr;
     p.svdw_accv = c.svdw_accv;
     p.svdw_tb_off = c.svdw_tb_off;
     p.dbg_info = nullptr;
@@ -463,10 +497,26 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     const int n_items = e->batch * p.n_level_edges;
     cudaError_t st = cudaSuccess;
     if (e->profile) cudaEventRecord(e->pev[0], e->stream);
-    st = launch_side_kernel<S>(false, c, p, n_items, e->stream);
+    int extra_launches = 0;
+    if constexpr (sizeof(S) == 8) {
+      if (c.lqc && only_edge < 0) {
+        // streaming CholeskyQR2 first; it flags the (item, side)s it cannot take and the Householder kernels below
+        // then process exactly those (every other CTA of theirs returns at once)
+        p.lq_flags = e->lq_flags;
+        st = launch_lq_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
+        ++extra_launches;
+      }
+    }
+    if (st == cudaSuccess) st = launch_side_kernel<S>(false, c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[1], e->stream);
     if (st == cudaSuccess) st = launch_k2<S>(c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[2], e->stream);
+    if constexpr (sizeof(S) == 8) {
+      if (st == cudaSuccess && p.lq_flags != nullptr) {
+        st = launch_rc_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
+        ++extra_launches;
+      }
+    }
     if (st == cudaSuccess) st = launch_k3<S>(c, p, n_items, e->stream);
     if (e->profile) {
       cudaEventRecord(e->pev[3], e->stream);
@@ -480,8 +530,8 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     if (st != cudaSuccess)
       return fail(e, TNSU_E_CUDA, "edge kernel launch (level %zu, MM=%d NC=%d nt=%d smem=%d/%d/%d): %s", lv, c.mm_t,
                   c.ncols, c.nt, c.smem_lq, c.smem_svd, c.smem_rc, cudaGetErrorString(st));
-    e->launches += 3;
-    e->last_n += 3;
+    e->launches += 3 + extra_launches;
+    e->last_n += 3 + extra_launches;
   }
   return TNSU_OK;
 }
@@ -722,6 +772,7 @@ int tnsu_destroy(tnsu_engine *e) {
   for (void *p : e->tens) cudaFree(p);
   for (void *p : e->ybuf) cudaFree(p);
   if (e->small) cudaFree(e->small);
+  if (e->lq_flags) cudaFree(e->lq_flags);
   for (int k = 0; k < 4; ++k)
     if (e->pev[k]) cudaEventDestroy(e->pev[k]);
   void *ptrs[] = {e->tnorm2, e->tticket, e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
@@ -805,6 +856,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_unrolled_lq = env && std::string(env) == "unrolled";
     env = getenv("TNSU_SVD_V");
     e->svd_accumulate_v = env && std::string(env) == "accumulate";
+    env = getenv("TNSU_LQ");
+    e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     env = getenv("TNSU_RC");
     e->force_simple_rc = env && std::string(env) == "simple";
     env = getenv("TNSU_RDM");

@@ -1,0 +1,520 @@
+// lq_chol.cuh — streaming K1 / K3 of the real float64 path: CholeskyQR2 on the FP64 tensor cores.
+//
+// Replaces, for well-conditioned bond matrices, the RQ reduction scipy.linalg.rq(P) (reference
+// src/tnsu/simple_update.py:243-250) and the recompose einsum r~ . Q (:274-275) with its inverse-weight absorption
+// (:290-291) and tensor_norm (:294-296).  Any orthonormal row basis Q is admissible for the reduction;
+// here P = L Q with L lower triangular from two Cholesky passes:
+//
+//   pass 1   G1 = P P^T (DMMA Gram, the pair-RDM loop)        G1 = L1 L1^T        W1 = L1^-1
+//   pass 2   Q1 = W1 P  (DMMA, P streamed a second time: L2 hits),   G2 = Q1 Q1^T = L2 L2^T      W2 = L2^-1
+//            L = L1 L2,   L^-1 = W2 W1
+//
+// The accumulator fragment of Q1 = W1 P (lane (g,t): rows 8I+g, columns 2t, 2t+1 of an 8-column tile) is, register
+// for register, the A AND the B fragment of the Gram update when the k index of the two k-steps is taken as column
+// 2t and 2t+1: no shuffle between the two products.  Orthogonality of Q is O(eps) as long as eps*cond(P)^2 << 1; the
+// kernel flags an (item, side) whose Cholesky breaks down or whose diag(L1) spans more than 1e5 (cond(P) >~ 1e5), and
+// the Householder kernels (lq_rolled_kernel / recompose_dmma_kernel) then process exactly the flagged ones.
+//
+// K3 needs no reflectors on this route:  P' = r~ Q = (r~ L^-1) P, and the environment weights that were absorbed into
+// P are divided out again right away, so  T'[:, c] = tscale * (r~ L^-1) T[:, c]:  one (d D' x d D_k) x (d D_k x N)
+// product straight from the OLD tensor into the NEW one, in place column tile by column tile.  The Y^H round trip
+// through HBM (half of the edge update's traffic) disappears.
+#pragma once
+#include "edge_update.cuh"
+
+#define LQC_THREADS 128
+#define LQC_CHUNK 512
+#define LQC_WL 32
+
+struct __align__(16) LqcCol {
+  double ws;  // product of the environment weights times the lazy tensor scale
+  int off;    // byte offset of (s = 0, x_k = 0) of this column
+  int pad;
+};
+struct __align__(16) LqcLeg {
+  int dim;
+  unsigned magic;
+  int stride;
+  int pad;
+};
+
+DEV void lqc_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+static inline int lqc_smem_bytes(int MB) {
+  const int MP = 8 * MB;
+  return LQC_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQC_WL * 8 + 5 * MP * (MP + 1) * 8 + 64;
+}
+
+// ---- small dense helpers, one warp, lane = row (or column) index, everything in registers -----------------------
+// Cholesky of the symmetric MP x MP matrix whose row `lane` is g[] (rows/cols >= M must hold the identity): on
+// return l[k] = L[lane][k] (zero above the diagonal), invd = 1 / L[lane][lane]; returns false on breakdown or when
+// diag(L) spans more than 1e5.
+template <int MP>
+DEV bool lqc_cholesky(double (&g)[MP], double (&l)[MP], double &invd, int lane, int M) {
+  bool ok = true;
+  double dmin = 1e300, dmax = 0.0;
+  invd = 1.0;
+#pragma unroll
+  for (int k = 0; k < MP; ++k) {
+    const double d = __shfl_sync(0xffffffffu, g[k], k);
+    if (k < M) ok = ok && (d > 0.0) && (d < 1e300);
+    const double dd = (d > 0.0) ? d : 1.0;
+    const double s = rsqrt(dd);
+    const double lkk = dd * s;
+    if (k < M) {
+      dmin = fmin(dmin, lkk);
+      dmax = fmax(dmax, lkk);
+    }
+    const double lk = (lane >= k) ? g[k] * s : 0.0;
+    l[k] = lk;
+    if (lane == k) invd = s;
+#pragma unroll
+    for (int j = k + 1; j < MP; ++j) {
+      const double lj = __shfl_sync(0xffffffffu, lk, j);
+      g[j] = fma(-lk, lj, g[j]);
+    }
+  }
+  return ok && (dmin > 1e-5 * dmax);
+}
+// x[r] = (L^-1)[r][lane] (column `lane` of the inverse) by forward substitution; l[] / invd as from lqc_cholesky
+template <int MP>
+DEV void lqc_tri_inverse(const double (&l)[MP], double invd, double (&x)[MP], int lane) {
+#pragma unroll
+  for (int r = 0; r < MP; ++r) {
+    double a0 = (r == lane) ? 1.0 : 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      const double lrk = __shfl_sync(0xffffffffu, l[k], r);  // L[r][k] lives in lane r
+      if (k & 1)
+        a1 = fma(-lrk, x[k], a1);
+      else
+        a0 = fma(-lrk, x[k], a0);
+    }
+    x[r] = (a0 + a1) * __shfl_sync(0xffffffffu, invd, r);
+  }
+}
+
+// =================================================================================================================
+// K1c: one CTA of 4 warps per (item, side)
+// =================================================================================================================
+template <int MB>
+__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) lq_chol_kernel(const EdgeLaunch<double> p, int *flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
+  const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+  const int b = item / p.n_level_edges;
+  const int ek = p.level_edges[item - b * p.n_level_edges];
+  if (p.active != nullptr && p.active[b] == 0) return;
+  const EdgeDesc &ed = p.descs[ek];
+  const SideDesc &sd = ed.s[side];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int M = sd.M, N = sd.N, Dk = ed.Dk, ldm = p.ldm;
+
+  LqcCol *cols = (LqcCol *)smem_raw;                  // [LQC_CHUNK]
+  LqcLeg *legs = (LqcLeg *)(cols + LQC_CHUNK);        // environment legs, innermost first
+  double *wl = (double *)(legs + TNSU_MAX_LEGS);      // [legs][LQC_WL]
+  double *G = wl + TNSU_MAX_LEGS * LQC_WL;            // [MP][LD] Gram matrix of the current pass
+  double *L1s = G + MP * LD, *W1s = L1s + MP * LD, *L2s = W1s + MP * LD, *W2s = L2s + MP * LD;
+  int *ok_s = (int *)(W2s + MP * LD);
+
+  const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
+  const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
+  for (int idx = tid; idx < TNSU_MAX_LEGS * LQC_WL; idx += LQC_THREADS) {
+    const int k = idx / LQC_WL, x = idx - k * LQC_WL;
+    int l = sd.nlegs - 1 - k;
+    if (l <= sd.bond_leg) --l;
+    double w = 1.0;
+    if (l >= 0) {
+      const int dim = sd.dims[l];
+      if (x < dim) w = wpoint[(size_t)sd.leg_edge[l] * p.dcap + x];
+      if (x == 0) {
+        LqcLeg L;
+        L.dim = dim;
+        L.magic = dim > 1 ? 0xFFFFFFFFu / (unsigned)dim + 1u : 0u;
+        L.stride = (int)sd.in_stride[l];
+        L.pad = 0;
+        legs[k] = L;
+      }
+    }
+    wl[idx] = w;
+  }
+  const int nenv = sd.nlegs - 1;
+  const char *tbase = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride);
+  auto row_ptr = [&](int r) {
+    const int rr = r < M ? r : 0;
+    const int s = rr / Dk, x = rr - s * Dk;
+    return tbase + 8 * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]);
+  };
+  auto build_table = [&](int c0) {
+    for (int cc = tid; cc < LQC_CHUNK; cc += LQC_THREADS) {
+      LqcCol e;
+      e.ws = 0.0;
+      e.off = 0;
+      e.pad = 0;
+      if (c0 + cc < N) {
+        unsigned rem = (unsigned)(c0 + cc);
+        double w = tsc;
+        unsigned off = 0;
+        for (int k = 0; k < nenv; ++k) {
+          const LqcLeg L = legs[k];
+          const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
+          const unsigned x = rem - qq * (unsigned)L.dim;
+          rem = qq;
+          off += x * (unsigned)L.stride;
+          w *= wl[k * LQC_WL + x];
+        }
+        e.ws = w;
+        e.off = (int)(off * 8u);
+      }
+      cols[cc] = e;
+    }
+  };
+  // sum the warps' partial Gram fragments in warp order into G (lower blocks), then mirror; pads with the identity
+  auto reduce_gram = [&](double (&acc)[NBLK][2]) {
+    for (int wv = 0; wv < LQC_THREADS / 32; ++wv) {
+      __syncthreads();
+      if (warp == wv) {
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < MB; ++I)
+#pragma unroll
+          for (int J = 0; J <= I; ++J, ++k) {
+            double *d0 = G + (8 * I + g) * LD + 8 * J + 2 * t;
+            if (wv == 0) {
+              d0[0] = acc[k][0];
+              d0[1] = acc[k][1];
+            } else {
+              d0[0] += acc[k][0];
+              d0[1] += acc[k][1];
+            }
+          }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < MP * MP; idx += LQC_THREADS) {
+      const int r = idx / MP, c = idx - r * MP;
+      if ((r >> 3) < (c >> 3)) G[r * LD + c] = G[c * LD + r];
+    }
+    __syncthreads();
+  };
+
+  // ------------------------------------------------------------------------------------------------ pass 1: G1 = P P^T
+  const char *rowp1[MB];
+#pragma unroll
+  for (int I = 0; I < MB; ++I) rowp1[I] = row_ptr(8 * I + g);
+  double acc[NBLK][2];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) acc[k][0] = acc[k][1] = 0.0;
+  for (int c0 = 0; c0 < N; c0 += LQC_CHUNK) {
+    __syncthreads();
+    build_table(c0);
+    __syncthreads();
+    const int nks = (min(LQC_CHUNK, N - c0) + 3) >> 2;
+#pragma unroll 2
+    for (int ks = warp; ks < nks; ks += LQC_THREADS / 32) {
+      const LqcCol e = cols[4 * ks + t];
+      double v[MB];
+#pragma unroll
+      for (int I = 0; I < MB; ++I) v[I] = __ldg((const double *)(rowp1[I] + (unsigned)e.off));
+      const double w2 = e.ws * e.ws;
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        const double a = v[I] * w2;
+#pragma unroll
+        for (int J = 0; J <= I; ++J, ++k) lqc_dmma(acc[k][0], acc[k][1], a, v[J]);
+      }
+    }
+  }
+  reduce_gram(acc);
+  // ------------------------------------------------------------------------------------------------ L1, W1 (warp 0)
+  double l1[MP];
+  if (warp == 0) {
+    double gr[MP], invd, x[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
+    const bool ok = lqc_cholesky<MP>(gr, l1, invd, lane, M);
+    lqc_tri_inverse<MP>(l1, invd, x, lane);
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        W1s[r * LD + lane] = x[r];       // column `lane` of W1
+        L1s[lane * LD + r] = l1[r];      // row `lane` of L1
+      }
+    }
+    if (lane == 0) ok_s[0] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (ok_s[0] == 0) {  // ill-conditioned: the Householder kernels take this (item, side)
+    if (tid == 0) flags[blockIdx.x] = 1;
+    return;
+  }
+  // ------------------------------------------------------------------------------------------------ pass 2: G2 = (W1 P)(W1 P)^T
+  double afr[MB][KS];
+#pragma unroll
+  for (int I = 0; I < MB; ++I)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int i = 8 * I + g, k = 4 * ks + t;
+      afr[I][ks] = (i < M && k < M) ? W1s[i * LD + k] : 0.0;
+    }
+  const char *rowp2[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) rowp2[ks] = row_ptr(4 * ks + t);
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) acc[k][0] = acc[k][1] = 0.0;
+  for (int c0 = 0; c0 < N; c0 += LQC_CHUNK) {
+    if (N > LQC_CHUNK) {  // the table of a single chunk is still valid
+      __syncthreads();
+      build_table(c0);
+      __syncthreads();
+    }
+    const int ntile = (min(LQC_CHUNK, N - c0) + 7) >> 3;
+#pragma unroll 2
+    for (int tl = warp; tl < ntile; tl += LQC_THREADS / 32) {
+      const unsigned off = (unsigned)cols[8 * tl + g].off;
+      double bv[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) bv[ks] = __ldg((const double *)(rowp2[ks] + off));
+      const double ws0 = cols[8 * tl + 2 * t].ws, ws1 = cols[8 * tl + 2 * t + 1].ws;
+      double q0[MB], q1[MB];
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) lqc_dmma(d0, d1, afr[I][ks], bv[ks]);
+        q0[I] = d0 * ws0;
+        q1[I] = d1 * ws1;
+      }
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < MB; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J, ++k) {
+          lqc_dmma(acc[k][0], acc[k][1], q0[I], q0[J]);
+          lqc_dmma(acc[k][0], acc[k][1], q1[I], q1[J]);
+        }
+    }
+  }
+  reduce_gram(acc);
+  // ------------------------------------------------------------------------------------------------ L2, W2, L = L1 L2, L^-1 = W2 W1
+  if (warp == 0) {
+    double gr[MP], l2[MP], invd, x[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
+    const bool ok = lqc_cholesky<MP>(gr, l2, invd, lane, M);
+    lqc_tri_inverse<MP>(l2, invd, x, lane);
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        W2s[r * LD + lane] = x[r];
+        L2s[lane * LD + r] = l2[r];
+      }
+    }
+    __syncwarp();
+    double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+    double *gL = small + (SM_L0 + side) * ldm * ldm;     // L  (M x M): what K2 reads
+    double *gW = small + (SM_S0 + side) * ldm * ldm;     // L^-1 (M x M): what the streaming K3 reads
+    if (lane < M) {
+      for (int j = 0; j < M; ++j) {  // j > lane: the loop below is empty and the strict upper triangle is zeroed
+        double a = 0.0, c = 0.0;
+        for (int k = j; k <= lane; ++k) {
+          a = fma(L1s[lane * LD + k], L2s[k * LD + j], a);  // (L1 L2)[lane][j]
+          c = fma(W2s[lane * LD + k], W1s[k * LD + j], c);  // (W2 W1)[lane][j]
+        }
+        gL[lane * ldm + j] = a;
+        gW[lane * ldm + j] = c;
+      }
+    }
+    if (lane == 0) flags[blockIdx.x] = ok ? 0 : 1;
+  }
+}
+
+// =================================================================================================================
+// K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one CTA of 4 warps per (item, side)
+// =================================================================================================================
+template <int MB>
+__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_kernel(const EdgeLaunch<double> p,
+                                                                                       const int *flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int MP = 8 * MB, KS = 2 * MB;
+  const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
+  const int b = item / p.n_level_edges;
+  const int ek = p.level_edges[item - b * p.n_level_edges];
+  if (p.active != nullptr && p.active[b] == 0) return;
+  if (flags[blockIdx.x] != 0) return;  // the Householder recompose owns this one
+  const EdgeDesc &ed = p.descs[ek];
+  const SideDesc &sd = ed.s[side];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int M = sd.M, N = sd.N, Mout = sd.Mout, Dk = ed.Dk, Dnew = ed.Dnew, ldm = p.ldm;
+
+  int *coff = (int *)smem_raw;                             // [LQC_CHUNK] byte offset of each column (same before / after)
+  LqcLeg *legs = (LqcLeg *)(coff + LQC_CHUNK);
+  double *matR = (double *)(legs + TNSU_MAX_LEGS);         // r~ (Mout x M)
+  double *matW = matR + ldm * ldm;                         // L^-1 (M x M)
+  double *matC = matW + ldm * ldm;                         // r~ L^-1
+  double *nred = matC + ldm * ldm;
+
+  if (tid < TNSU_MAX_LEGS) {
+    int l = sd.nlegs - 1 - tid;
+    if (l <= sd.bond_leg) --l;
+    if (l >= 0) {
+      LqcLeg L;
+      L.dim = sd.dims[l];
+      L.magic = L.dim > 1 ? 0xFFFFFFFFu / (unsigned)L.dim + 1u : 0u;
+      L.stride = (int)sd.in_stride[l];
+      L.pad = 0;
+      legs[tid] = L;
+    }
+  }
+  const double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+  const double *gR = small + (SM_R0 + side) * ldm * ldm;
+  const double *gW = small + (SM_S0 + side) * ldm * ldm;
+  for (int idx = tid; idx < Mout * ldm; idx += LQC_THREADS) matR[idx] = gR[idx];
+  for (int idx = tid; idx < M * ldm; idx += LQC_THREADS) matW[idx] = gW[idx];
+  const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
+  __syncthreads();
+  for (int idx = tid; idx < Mout * M; idx += LQC_THREADS) {
+    const int i = idx / M, j = idx - i * M;
+    double a0 = 0.0, a1 = 0.0;
+    int k = j;
+    for (; k + 1 < M; k += 2) {
+      a0 = fma(matR[i * ldm + k], matW[k * ldm + j], a0);
+      a1 = fma(matR[i * ldm + k + 1], matW[(k + 1) * ldm + j], a1);
+    }
+    if (k < M) a0 = fma(matR[i * ldm + k], matW[k * ldm + j], a0);
+    matC[i * ldm + j] = (a0 + a1) * tsc;
+  }
+  __syncthreads();
+  double afr[MB][KS];
+#pragma unroll
+  for (int I = 0; I < MB; ++I)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int i = 8 * I + g, k = 4 * ks + t;
+      afr[I][ks] = (i < Mout && k < M) ? matC[i * ldm + k] : 0.0;
+    }
+  char *tbase = (char *)((double *)sd.base + (size_t)b * sd.point_stride);
+  const char *rowin[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int r = 4 * ks + t < M ? 4 * ks + t : 0;
+    const int s = r / Dk, x = r - s * Dk;
+    rowin[ks] = tbase + 8 * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]);
+  }
+  long long rowout[MB];
+#pragma unroll
+  for (int I = 0; I < MB; ++I) {
+    const int r = 8 * I + g < Mout ? 8 * I + g : 0;
+    const int s = r / Dnew, x = r - s * Dnew;
+    rowout[I] = 8 * ((long long)s * sd.out_stride_phys + (long long)x * sd.out_stride[sd.bond_leg]);
+  }
+  const int nenv = sd.nlegs - 1;
+  double n2 = 0.0;
+  for (int c0 = 0; c0 < N; c0 += LQC_CHUNK) {
+    __syncthreads();
+    for (int cc = tid; cc < LQC_CHUNK; cc += LQC_THREADS) {
+      unsigned off = 0;
+      if (c0 + cc < N) {
+        unsigned rem = (unsigned)(c0 + cc);
+        for (int k = 0; k < nenv; ++k) {
+          const LqcLeg L = legs[k];
+          const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
+          off += (rem - qq * (unsigned)L.dim) * (unsigned)L.stride;
+          rem = qq;
+        }
+      }
+      coff[cc] = (int)(off * 8u);
+    }
+    __syncthreads();
+    const int ncols = min(LQC_CHUNK, N - c0);
+    const int ntile = (ncols + 7) >> 3;
+#pragma unroll 2
+    for (int tl = warp; tl < ntile; tl += LQC_THREADS / 32) {
+      // the whole (M x 8) input tile is in registers before the first element of the output tile is stored
+      const unsigned off = (unsigned)coff[min(8 * tl + g, ncols - 1)];
+      double bv[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) bv[ks] = *(const volatile double *)(rowin[ks] + off);
+      const int ca = 8 * tl + 2 * t;
+      const unsigned o0 = (unsigned)coff[min(ca, ncols - 1)], o1 = (unsigned)coff[min(ca + 1, ncols - 1)];
+      double d0[MB], d1[MB];
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        d0[I] = d1[I] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) lqc_dmma(d0[I], d1[I], afr[I][ks], bv[ks]);
+      }
+      __syncwarp();  // every lane of the warp has its inputs: the stores below overwrite the same tile
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        if (8 * I + g < Mout) {
+          if (ca < ncols) {
+            n2 = fma(d0[I], d0[I], n2);
+            *(double *)(tbase + rowout[I] + o0) = d0[I];
+          }
+          if (ca + 1 < ncols) {
+            n2 = fma(d1[I], d1[I], n2);
+            *(double *)(tbase + rowout[I] + o1) = d1[I];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, m);
+  if (lane == 0) nred[warp] = n2;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < LQC_THREADS / 32; ++w) tot += nred[w];
+    p.tscale[(size_t)b * p.n_tensors + sd.tensor] = 1.0 / sqrt(tot);
+  }
+}
+
+static inline int rcc_smem_bytes(int ldm) { return LQC_CHUNK * 4 + TNSU_MAX_LEGS * 16 + 3 * ldm * ldm * 8 + 64; }
+
+template <int MB>
+cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flags, cudaStream_t st) {
+  auto kern = lq_chol_kernel<MB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+    if (s != cudaSuccess) return s;
+    attr_done = true;
+  }
+  kern<<<2 * n_items, LQC_THREADS, lqc_smem_bytes(MB), st>>>(p, flags);
+  return cudaGetLastError();
+}
+template <int MB>
+cudaError_t launch_rc_chol_v(const EdgeLaunch<double> &p, int n_items, const int *flags, cudaStream_t st) {
+  auto kern = recompose_chol_kernel<MB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+    if (s != cudaSuccess) return s;
+    attr_done = true;
+  }
+  kern<<<2 * n_items, LQC_THREADS, rcc_smem_bytes(p.ldm), st>>>(p, flags);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_lq_chol(const EdgeLaunch<double> &p, int n_items, int m_max, int *flags, cudaStream_t st) {
+  const int mb = (m_max + 7) / 8;
+  if (mb == 1) return launch_lq_chol_v<1>(p, n_items, flags, st);
+  if (mb == 2) return launch_lq_chol_v<2>(p, n_items, flags, st);
+  if (mb == 3) return launch_lq_chol_v<3>(p, n_items, flags, st);
+  return launch_lq_chol_v<4>(p, n_items, flags, st);
+}
+inline cudaError_t launch_rc_chol(const EdgeLaunch<double> &p, int n_items, int m_max, const int *flags, cudaStream_t st) {
+  const int mb = (m_max + 7) / 8;
+  if (mb == 1) return launch_rc_chol_v<1>(p, n_items, flags, st);
+  if (mb == 2) return launch_rc_chol_v<2>(p, n_items, flags, st);
+  if (mb == 3) return launch_rc_chol_v<3>(p, n_items, flags, st);
+  return launch_rc_chol_v<4>(p, n_items, flags, st);
+}

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(RCD_THREADS, (MBO * KB <= 4) ? 4 : 3) recompos
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.lq_flags != nullptr && p.lq_flags[blockIdx.x / CL] == 0) return;  // recomposed by recompose_chol_kernel
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
   const int lt = threadIdx.x, lane = lt & 31, warp = lt >> 5;
