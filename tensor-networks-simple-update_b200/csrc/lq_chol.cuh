@@ -102,7 +102,7 @@ DEV void lqc_tri_inverse(const double (&l)[MP], double invd, double (&x)[MP], in
 // K1c: one CTA of 4 warps per (item, side)
 // =================================================================================================================
 template <int MB>
-__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) lq_chol_kernel(const EdgeLaunch<double> p, int *flags) {
+__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 5 : 2) lq_chol_kernel(const EdgeLaunch<double> p, int *flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
   const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) lq_chol_kernel(c
     build_table(c0);
     __syncthreads();
     const int nks = (min(LQC_CHUNK, N - c0) + 3) >> 2;
-#pragma unroll 2
+#pragma unroll 4
     for (int ks = warp; ks < nks; ks += LQC_THREADS / 32) {
       const LqcCol e = cols[4 * ks + t];
       double v[MB];
@@ -316,22 +316,32 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) lq_chol_kernel(c
         L2s[lane * LD + r] = l2[r];
       }
     }
-    __syncwarp();
+    if (lane == 0) ok_s[0] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  // L = L1 L2 (what K2 reads) and L^-1 = W2 W1 (what the streaming K3 reads), all threads, strict upper triangle zeroed
+  {
     double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
-    double *gL = small + (SM_L0 + side) * ldm * ldm;     // L  (M x M): what K2 reads
-    double *gW = small + (SM_S0 + side) * ldm * ldm;     // L^-1 (M x M): what the streaming K3 reads
-    if (lane < M) {
-      for (int j = 0; j < M; ++j) {  // j > lane: the loop below is empty and the strict upper triangle is zeroed
-        double a = 0.0, c = 0.0;
-        for (int k = j; k <= lane; ++k) {
-          a = fma(L1s[lane * LD + k], L2s[k * LD + j], a);  // (L1 L2)[lane][j]
-          c = fma(W2s[lane * LD + k], W1s[k * LD + j], c);  // (W2 W1)[lane][j]
-        }
-        gL[lane * ldm + j] = a;
-        gW[lane * ldm + j] = c;
+    double *gL = small + (SM_L0 + side) * ldm * ldm;
+    double *gW = small + (SM_S0 + side) * ldm * ldm;
+    for (int idx = tid; idx < M * M; idx += LQC_THREADS) {
+      const int r = idx / M, j = idx - r * M;
+      double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+      int k = j;
+      for (; k + 1 <= r; k += 2) {
+        a0 = fma(L1s[r * LD + k], L2s[k * LD + j], a0);
+        a1 = fma(L1s[r * LD + k + 1], L2s[(k + 1) * LD + j], a1);
+        c0 = fma(W2s[r * LD + k], W1s[k * LD + j], c0);
+        c1 = fma(W2s[r * LD + k + 1], W1s[(k + 1) * LD + j], c1);
       }
+      if (k <= r) {
+        a0 = fma(L1s[r * LD + k], L2s[k * LD + j], a0);
+        c0 = fma(W2s[r * LD + k], W1s[k * LD + j], c0);
+      }
+      gL[r * ldm + j] = a0 + a1;
+      gW[r * ldm + j] = c0 + c1;
     }
-    if (lane == 0) flags[blockIdx.x] = ok ? 0 : 1;
+    if (tid == 0) flags[blockIdx.x] = ok_s[0] ? 0 : 1;
   }
 }
 
