@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     if (lt == 0 && (int)blockIdx.x < n_work) issue(blockIdx.x);
   }
 
-  for (int w = (int)(blockIdx.x / CL); w < n_work; w += (STREAM ? (int)gridDim.x : n_work)) {
+  // one work item per CTA, except the persistent variants: STREAM, and the fallback behind the streaming
+  // CholeskyQR2 kernel (lq_flags), where a small grid scans the flags and factors only the flagged (item, side)s
+  const bool looped = STREAM || (!CLUSTER && p.lq_flags != nullptr);
+  for (int w = (int)(blockIdx.x / CL); w < n_work; w += (looped ? (int)gridDim.x : n_work)) {
   const int item = w >> 1;
   const int side = w & 1;
   const int b = item / p.n_level_edges;
@@ -490,11 +493,12 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
       if (lt == 0 && w + (int)gridDim.x < n_work) issue(w + gridDim.x);
       continue;
     } else {
+      if (looped) continue;
       return;
     }
   }
 
-  if (p.lq_flags != nullptr && p.lq_flags[w] == 0) return;  // factored by the streaming CholeskyQR2 kernel already
+  if (p.lq_flags != nullptr && p.lq_flags[w] == 0) continue;  // factored by the streaming CholeskyQR2 kernel already
 
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
     const int r = idx / K, qq = idx - r * K;
     gL[r * ldm + qq] = matL[r * ldm + qq];
   }
-  if constexpr (STREAM) __syncthreads();  // the shared matrices are reused by the next work item
+  if (looped) __syncthreads();  // the shared matrices are reused by the next work item
   }  // work loop
 }
 
@@ -1230,7 +1234,8 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
     if (s != cudaSuccess) return s;
     attr_done = true;
   }
-  kern<<<2 * n_items, p.nt, p.smem_lq, st>>>(p);
+  const int grid = (p.lq_flags != nullptr && 2 * n_items > 1184) ? 1184 : 2 * n_items;  // fallback scan: 8 CTAs per SM
+  kern<<<grid, p.nt, p.smem_lq, st>>>(p);
   return cudaGetLastError();
 }
 
