@@ -22,7 +22,8 @@
 #pragma once
 #include "edge_update.cuh"
 
-#define LQC_THREADS 128
+#define LQC_THREADS 64   // K1c: two warps per (item, side) — the Cholesky phases keep one of them idle, not three
+#define RCC_THREADS 128  // K3c
 #define LQC_CHUNK 512
 #define LQC_WL 32
 
@@ -102,7 +103,7 @@ DEV void lqc_tri_inverse(const double (&l)[MP], double invd, double (&x)[MP], in
 // K1c: one CTA of 4 warps per (item, side)
 // =================================================================================================================
 template <int MB>
-__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 5 : 2) lq_chol_kernel(const EdgeLaunch<double> p, int *flags) {
+__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(const EdgeLaunch<double> p, int *flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
   const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 5 : 2) lq_chol_kernel(c
 // K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one CTA of 4 warps per (item, side)
 // =================================================================================================================
 template <int MB>
-__global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_kernel(const EdgeLaunch<double> p,
+__global__ void __launch_bounds__(RCC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_kernel(const EdgeLaunch<double> p,
                                                                                        const int *flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, KS = 2 * MB;
@@ -386,11 +387,11 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
   const double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
   const double *gR = small + (SM_R0 + side) * ldm * ldm;
   const double *gW = small + (SM_S0 + side) * ldm * ldm;
-  for (int idx = tid; idx < Mout * ldm; idx += LQC_THREADS) matR[idx] = gR[idx];
-  for (int idx = tid; idx < M * ldm; idx += LQC_THREADS) matW[idx] = gW[idx];
+  for (int idx = tid; idx < Mout * ldm; idx += RCC_THREADS) matR[idx] = gR[idx];
+  for (int idx = tid; idx < M * ldm; idx += RCC_THREADS) matW[idx] = gW[idx];
   const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
   __syncthreads();
-  for (int idx = tid; idx < Mout * M; idx += LQC_THREADS) {
+  for (int idx = tid; idx < Mout * M; idx += RCC_THREADS) {
     const int i = idx / M, j = idx - i * M;
     double a0 = 0.0, a1 = 0.0;
     int k = j;
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
   double n2 = 0.0;
   for (int c0 = 0; c0 < N; c0 += LQC_CHUNK) {
     __syncthreads();
-    for (int cc = tid; cc < LQC_CHUNK; cc += LQC_THREADS) {
+    for (int cc = tid; cc < LQC_CHUNK; cc += RCC_THREADS) {
       unsigned off = 0;
       if (c0 + cc < N) {
         unsigned rem = (unsigned)(c0 + cc);
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
     const int ncols = min(LQC_CHUNK, N - c0);
     const int ntile = (ncols + 7) >> 3;
 #pragma unroll 2
-    for (int tl = warp; tl < ntile; tl += LQC_THREADS / 32) {
+    for (int tl = warp; tl < ntile; tl += RCC_THREADS / 32) {
       // the whole (M x 8) input tile is in registers before the first element of the output tile is stored
       const unsigned off = (unsigned)coff[min(8 * tl + g, ncols - 1)];
       double bv[KS];
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
   __syncthreads();
   if (tid == 0) {
     double tot = 0.0;
-    for (int w = 0; w < LQC_THREADS / 32; ++w) tot += nred[w];
+    for (int w = 0; w < RCC_THREADS / 32; ++w) tot += nred[w];
     p.tscale[(size_t)b * p.n_tensors + sd.tensor] = 1.0 / sqrt(tot);
   }
 }
@@ -511,7 +512,7 @@ cudaError_t launch_rc_chol_v(const EdgeLaunch<double> &p, int n_items, const int
     if (s != cudaSuccess) return s;
     attr_done = true;
   }
-  kern<<<2 * n_items, LQC_THREADS, rcc_smem_bytes(p.ldm), st>>>(p, flags);
+  kern<<<2 * n_items, RCC_THREADS, rcc_smem_bytes(p.ldm), st>>>(p, flags);
   return cudaGetLastError();
 }
 inline cudaError_t launch_lq_chol(const EdgeLaunch<double> &p, int n_items, int m_max, int *flags, cudaStream_t st) {
