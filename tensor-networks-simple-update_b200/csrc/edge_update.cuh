@@ -79,6 +79,7 @@ struct EdgeLaunch {
   int svdw_precond;          // pivoted-QR preconditioner before the Jacobi iteration
   int svdw_ldt;              // leading dimension of its transpose buffer
   const int *lq_flags;       // streaming K1/K3 (lq_chol.cuh) ran first: per (item, side) 1 = the Householder kernels must process it, 0 = skip; nullptr = process all
+  int lqc_force_fallback;    // TNSU_LQ=fallback: the streaming kernel flags every (item, side) (tests of the fallback path)
   int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;

@@ -82,6 +82,7 @@ struct tnsu_engine {
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
   bool force_householder = false;         // TNSU_LQ=householder: no streaming CholeskyQR2 K1/K3 in front of the Householder kernels (A/B comparisons)
+  bool lqc_force_fallback = false;        // TNSU_LQ=fallback: streaming kernel flags everything, the Householder fallback does all the work (tests)
   int *lq_flags = nullptr;                // [batch * max_level_size * 2] per (item, side): 1 = Householder kernels must process it
   bool force_simple_rc = false;           // TNSU_RC=simple: register-column K3 (recompose_kernel) instead of the tensor-core one (A/B comparisons)
   bool force_simple_rdm = false;          // TNSU_RDM=simple: shared-memory-staged pair RDM kernel instead of the DMMA one (A/B comparisons)
@@ -314,9 +315,11 @@ static int plan_sweep(tnsu_engine *e) {
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
     if (!cx && !e->force_householder && !e->force_simple_rc && !e->lq_stream && !e->force_unrolled_lq && e->dcap <= 32 &&
-        c.cluster == 1) {
+        c.cluster == 1 && maxN >= 256) {
       // streaming K1/K3: every side of the level must have M <= N, an unchanged bond dimension (the recompose runs in
-      // place) and tensors below 2 GiB (32-bit byte offsets)
+      // place) and tensors below 2 GiB (32-bit byte offsets).  Narrow bond matrices (N < 256: the D <= 4 networks of the
+      // sweep metric) stay with the Householder kernels: there a launch is latency bound, and two Cholesky chains plus
+      // two more launches per level cost more than they save (measured: 570 vs 531 us per sweep at D = 4, 256 points)
       bool ok_lqc = true;
       int mm = 1;
       for (int ek : e->level_edges[lv]) {
@@ -486,6 +489,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_precond = c.svdw_precond;
     p.svdw_ldt = c.svdw_ldt;
     p.lq_flags = nullptr;
+    p.lqc_force_fallback = e->lqc_force_fallback ? 1 : 0;
     p.svdw_accv = c.svdw_accv;
     p.svdw_tb_off = c.svdw_tb_off;
     p.dbg_info = nullptr;
@@ -858,6 +862,7 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->svd_accumulate_v = env && std::string(env) == "accumulate";
     env = getenv("TNSU_LQ");
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
+    e->lqc_force_fallback = env && std::string(env) == "fallback";
     env = getenv("TNSU_RC");
     e->force_simple_rc = env && std::string(env) == "simple";
     env = getenv("TNSU_RDM");

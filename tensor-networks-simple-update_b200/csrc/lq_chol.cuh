@@ -110,6 +110,10 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.lqc_force_fallback) {
+    if (threadIdx.x == 0) flags[blockIdx.x] = 1;
+    return;
+  }
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -173,12 +173,14 @@ def test_unsupported_shapes_fail_loudly(tnsu):
 def test_svd_kernels_agree(tnsu, monkeypatch):
     """The register-resident warp SVD (V-free with recovered right vectors = the default, with accumulated V, without
     the pivoted-QR preconditioner) and the shared-memory Jacobi kernel are interchangeable, and so are the tensor-core
-    and the register-column K3: same weights and energy on the BASELINE config-2 shape."""
+    and the register-column K3, and the streaming CholeskyQR2 K1/K3 (default at this shape), the Householder K1/K3 alone
+    (TNSU_LQ=householder) and the Householder kernels as the flagged fallback behind the streaming one
+    (TNSU_LQ=fallback): same weights and energy on the BASELINE config-2 shape."""
     smat = tnsu.smc.infinite_structure_matrix_dict("peps")
     sx, sy, sz = tnsu.spin_operators(0.5)
     results = []
     for env in ({}, {"TNSU_SVD_V": "accumulate"}, {"TNSU_SVD_PRECOND": "0"}, {"TNSU_SVD": "smem"}, {"TNSU_LQ": "unrolled"},
-                {"TNSU_RC": "simple"}):
+                {"TNSU_RC": "simple"}, {"TNSU_LQ": "householder"}, {"TNSU_LQ": "fallback"}):
         for k in ("TNSU_SVD_PRECOND", "TNSU_SVD", "TNSU_LQ", "TNSU_SVD_V", "TNSU_RC"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -227,6 +229,38 @@ def test_pair_rdm_kernels_agree(tnsu, monkeypatch, lattice, dim, d):
     assert abs(results[0][0] - results[1][0]) < 1e-12 * max(1.0, abs(results[1][0]))
     for a, b in zip(results[0][1], results[1][1]):
         assert np.abs(a - b).max() < 1e-12
+
+
+def test_streaming_lq_flags_ill_conditioned_points(tnsu):
+    """The streaming CholeskyQR2 K1/K3 (lq_chol.cuh) only keeps bond matrices whose Cholesky factor spans less than
+    1e5 on its diagonal; the others are flagged and taken by the Householder kernels in the same level.  A batch that
+    mixes a well-conditioned point with one whose tensors have a 1e-8 slice on every leg (cond(P) ~ 1e8) must match
+    the oracle (reference simple_update.py:219-296) on both."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    nets = []
+    for k in range(2):
+        np.random.seed(300 + k)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+        if k == 1:
+            scale = np.ones(8)
+            scale[7] = 1e-8
+            tn.tensors = [t * scale[None, :, None, None, None] * scale[None, None, :, None, None] *
+                          scale[None, None, None, :, None] * scale[None, None, None, None, :] for t in tn.tensors]
+        nets.append(tn)
+    ref = [tn.copy() for tn in nets]
+    batch = tnsu.SimpleUpdateBatch(nets, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=8, max_iterations=2,
+                                   convergence_error=1e-30)
+    batch.run()
+    energies = batch.energy_per_site()
+    model = orc.Model([1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [])
+    for k in range(2):
+        t, w = [np.array(x) for x in ref[k].tensors], [np.array(x) for x in ref[k].weights]
+        orc.run(t, w, smat, model, [0.05], 8, 2, 1e-30)
+        for a, b in zip(w, nets[k].weights):
+            assert np.abs(a - b).max() < TOL_W
+        e_ref = orc.energy_per_site(t, w, smat, model)
+        assert abs(e_ref - energies[k]) < TOL_E * max(1.0, abs(e_ref))
 
 
 def test_batch_matches_single_and_oracle(tnsu):
