@@ -199,6 +199,48 @@ def svd_preconditioned(theta):
     return u, sv, acc.T, sweeps
 
 
+def cholesky_lower_and_inverse(g, span=1e-5):
+    """Right-looking Cholesky G = L L^T with the checks of lq_chol_kernel: returns (L, L^-1) or None on a non-positive
+    pivot or when diag(L) spans more than 1/span (cond(P) too large for CholeskyQR2: the Householder kernels take it)."""
+    g = np.array(g, dtype=float)
+    m = g.shape[0]
+    low = np.zeros_like(g)
+    for k in range(m):
+        d = g[k, k]
+        if not (0.0 < d < 1e300):
+            return None
+        lkk = np.sqrt(d)
+        low[k:, k] = g[k:, k] / lkk
+        g[k + 1:, k + 1:] -= np.outer(low[k + 1:, k], low[k + 1:, k])
+    diag = np.diag(low)
+    if not diag.min() > span * diag.max():
+        return None
+    inv = np.zeros_like(low)
+    for j in range(m):  # forward substitution, column by column
+        for r in range(j, m):
+            acc = (1.0 if r == j else 0.0) - low[r, j:r] @ inv[j:r, j]
+            inv[r, j] = acc / low[r, r]
+    return low, inv
+
+
+def cholqr2_lq(p):
+    """P = L Q the way lq_chol_kernel computes it: G1 = P P^T = L1 L1^T, Q1 = L1^-1 P, G2 = Q1 Q1^T = L2 L2^T,
+    L = L1 L2, L^-1 = L2^-1 L1^-1.  Returns (L, L^-1) or None when the kernel would flag the matrix."""
+    p = np.array(p, dtype=float)
+    if p.shape[0] > p.shape[1]:
+        return None
+    first = cholesky_lower_and_inverse(p @ p.T)
+    if first is None:
+        return None
+    l1, w1 = first
+    q1 = w1 @ p
+    second = cholesky_lower_and_inverse(q1 @ q1.T)
+    if second is None:
+        return None
+    l2, w2 = second
+    return l1 @ l2, w2 @ w1
+
+
 def svd_vfree(theta, keep):
     """The default K2 route (svd_warp_kernel<R, false>): pivoted QR of theta^T, odd-even Jacobi on X = R~^T WITHOUT
     an accumulator, the `keep` largest columns give sigma and u = x / sigma; the matching right vectors are recovered

@@ -111,3 +111,68 @@ def test_vfree_svd_properties():
     assert np.abs(s[:2] - np.linalg.svd(a, compute_uv=False)[:2]).max() < 1e-12 and s[2:].max() < 1e-12
     assert np.abs(wt @ wt.T - np.eye(6)).max() < 1e-12
     assert np.abs((u[:, :2] * s[:2]) @ wt[:2] - a).max() < 1e-12
+
+
+def test_cholqr2_lq_properties():
+    """The streaming K1 route (lq_chol.cuh, device_model.cholqr2_lq): for cond(P) up to ~1e5 the two Cholesky passes give
+    P = L Q with Q = L^-1 P orthonormal to a few 1e-13 and L lower triangular; beyond that (or for more rows than
+    columns) the route declines and the Householder kernels are used."""
+    rng = np.random.default_rng(11)
+    for m, n, cond in ((16, 512, 1e1), (16, 512, 1e3), (16, 512, 5e4), (12, 1024, 1e2), (8, 64, 1e2)):
+        u, _ = np.linalg.qr(rng.normal(size=(m, m)))
+        v, _ = np.linalg.qr(rng.normal(size=(n, m)))
+        p = (u * np.logspace(0, -np.log10(cond), m)) @ v.T
+        out = dm.cholqr2_lq(p)
+        assert out is not None, (m, n, cond)
+        low, inv = out
+        q = inv @ p
+        assert np.abs(q @ q.T - np.eye(m)).max() < 5e-13
+        assert np.abs(low @ q - p).max() < 1e-13 * np.abs(p).max()
+        assert np.abs(np.triu(low, 1)).max() == 0.0
+    u, _ = np.linalg.qr(rng.normal(size=(16, 16)))
+    v, _ = np.linalg.qr(rng.normal(size=(512, 16)))
+    assert dm.cholqr2_lq((u * np.logspace(0, -9, 16)) @ v.T) is None      # cond 1e9: flagged
+    assert dm.cholqr2_lq(rng.normal(size=(12, 5))) is None                 # M > N: flagged
+
+
+def test_cholqr2_route_matches_oracle_and_recompose_identity():
+    """One edge update with the streaming route — L from CholeskyQR2, recompose T'[:, c] = (r~ L^-1) T[:, c] with the
+    environment weights cancelling — equals the oracle's RQ route on weights and energy (peps D=4 state, 2 sweeps)."""
+    case = build_case("tfi_D4")
+    smat = case["smat"]
+    np.random.seed(case["seed"])
+    tensors, weights = orc.random_network(smat, case["d"], case["virtual_dim"])
+    t2, w2 = [t.copy() for t in tensors], [w.copy() for w in weights]
+    model = orc.Model(case["j_ij"], case["h_k"], case["s_i"], case["s_j"], case["s_k"], case["hamiltonian"])
+    di, dj = model.dims
+    from scipy import linalg
+    for _ in range(2):
+        orc.sweep(tensors, weights, smat, model, case["dt"], case["d_max"])
+        for ek in range(smat.shape[1]):
+            gate = np.real(orc.ite_gate(model.edge_hamiltonian(smat, ek), case["dt"], di, dj))
+            ti, ai, tj, aj = orc.edge_endpoints(smat, ek)
+            lam = w2[ek]
+            facs = []
+            for t in (ti, tj):
+                p, shape = dm.bond_matrix(t2[t], w2, smat, t, ek)
+                low, inv = dm.cholqr2_lq(np.real(p))
+                facs.append((low, inv, shape))
+            (l_i, inv_i, sh_i), (l_j, inv_j, sh_j) = facs
+            dk = len(lam)
+            theta = np.einsum("ieq,e,jep,ijab->qabp", np.reshape(l_i, (di, dk, -1)), lam, np.reshape(l_j, (dj, dk, -1)), gate)
+            k_i, k_j = l_i.shape[1], l_j.shape[1]
+            u, s, vh = linalg.svd(np.reshape(theta, (k_i * di, dj * k_j)), full_matrices=False)
+            d_new = min(case["d_max"], len(s))
+            u, s, vh = u[:, :d_new], s[:d_new], vh[:d_new]
+            rt_i = np.reshape(np.transpose(np.reshape(u, (k_i, di, d_new)), (1, 2, 0)), (di * d_new, k_i))
+            rt_j = np.reshape(np.transpose(np.reshape(vh, (d_new, dj, k_j)), (1, 0, 2)), (dj * d_new, k_j))
+            for t, a, rt, inv, sh in ((ti, ai, rt_i, inv_i, sh_i), (tj, aj, rt_j, inv_j, sh_j)):
+                raw = np.reshape(np.moveaxis(np.real(t2[t]), a, 1), (sh[0] * sh[1], -1))   # T itself: no weights
+                new_shape = list(sh)
+                new_shape[1] = d_new
+                out = np.moveaxis(np.reshape((rt @ inv) @ raw, new_shape), 1, a)
+                t2[t] = out / np.sqrt(np.sum(out * out))
+            w2[ek] = s / np.sum(s)
+        for a, b in zip(weights, w2):
+            assert np.abs(a - b).max() < 1e-12
+        assert abs(orc.energy_per_site(tensors, weights, smat, model) - orc.energy_per_site(t2, w2, smat, model)) < 1e-12
