@@ -82,6 +82,7 @@ struct tnsu_engine {
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
   bool force_householder = false;         // TNSU_LQ=householder: no streaming CholeskyQR2 K1/K3 in front of the Householder kernels (A/B comparisons)
+  bool lqc_cta_kernel = false;            // TNSU_LQ=cta: two-warp-CTA streaming K1 instead of the one-warp-per-matrix kernel (A/B comparisons)
   bool lqc_force_fallback = false;        // TNSU_LQ=fallback: streaming kernel flags everything, the Householder fallback does all the work (tests)
   int *lq_flags = nullptr;                // [batch * max_level_size * 2] per (item, side): 1 = Householder kernels must process it
   bool force_simple_rc = false;           // TNSU_RC=simple: register-column K3 (recompose_kernel) instead of the tensor-core one (A/B comparisons)
@@ -489,7 +490,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_precond = c.svdw_precond;
     p.svdw_ldt = c.svdw_ldt;
     p.lq_flags = nullptr;
-    p.lqc_force_fallback = e->lqc_force_fallback ? 1 : 0;
+    p.lqc_force_fallback = e->lqc_force_fallback ? 1 : (e->lqc_cta_kernel ? 2 : 0);
     p.svdw_accv = c.svdw_accv;
     p.svdw_tb_off = c.svdw_tb_off;
     p.dbg_info = nullptr;
@@ -863,6 +864,7 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     env = getenv("TNSU_LQ");
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     e->lqc_force_fallback = env && std::string(env) == "fallback";
+    e->lqc_cta_kernel = env && std::string(env) == "cta";
     env = getenv("TNSU_RC");
     e->force_simple_rc = env && std::string(env) == "simple";
     env = getenv("TNSU_RDM");

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
-  if (p.lqc_force_fallback) {
+  if (p.lqc_force_fallback == 1) {
     if (threadIdx.x == 0) flags[blockIdx.x] = 1;
     return;
   }
@@ -351,6 +351,265 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
 }
 
 // =================================================================================================================
+// K1c, one WARP per (item, side): no block barrier, no idle warp during the Cholesky chains — the four warps of a CTA
+// are four independent factorisations whose serial phases hide behind each other's DMMAs
+// =================================================================================================================
+#define LQW_WARPS 4
+#define LQW_CHUNK 128
+#define LQW_WL 16
+
+static inline int lqw_smem_bytes_per_warp(int MB) {
+  const int MP = 8 * MB;
+  return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + 4 * MP * (MP + 1) * 8 + 16;
+}
+
+template <int MB>
+__global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_kernel(const EdgeLaunch<double> p, int *flags,
+                                                                                        int smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x * LQW_WARPS + warp;  // work item = (item, side)
+  const int n_work = 2 * p.batch * p.n_level_edges;
+  if (w >= n_work) return;
+  const int item = w >> 1, side = w & 1;
+  const int b = item / p.n_level_edges;
+  const int ek = p.level_edges[item - b * p.n_level_edges];
+  if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.lqc_force_fallback == 1) {
+    if (lane == 0) flags[w] = 1;
+    return;
+  }
+  const EdgeDesc &ed = p.descs[ek];
+  const SideDesc &sd = ed.s[side];
+  const int g = lane >> 2, t = lane & 3;
+  const int M = sd.M, N = sd.N, Dk = ed.Dk, ldm = p.ldm;
+
+  unsigned char *mine = smem_raw + (size_t)warp * smem_per_warp;
+  LqcCol *cols = (LqcCol *)mine;                      // [LQW_CHUNK]
+  LqcLeg *legs = (LqcLeg *)(cols + LQW_CHUNK);
+  double *wl = (double *)(legs + TNSU_MAX_LEGS);      // [legs][LQW_WL]
+  double *G = wl + TNSU_MAX_LEGS * LQW_WL;            // Gram matrix of the current pass, later L2
+  double *L1s = G + MP * LD, *W1s = L1s + MP * LD, *W2s = W1s + MP * LD;
+
+  const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
+  const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
+  for (int idx = lane; idx < TNSU_MAX_LEGS * LQW_WL; idx += 32) {
+    const int k = idx / LQW_WL, x = idx - k * LQW_WL;
+    int l = sd.nlegs - 1 - k;
+    if (l <= sd.bond_leg) --l;
+    double wv = 1.0;
+    if (l >= 0) {
+      const int dim = sd.dims[l];
+      if (x < dim) wv = wpoint[(size_t)sd.leg_edge[l] * p.dcap + x];
+      if (x == 0) {
+        LqcLeg L;
+        L.dim = dim;
+        L.magic = dim > 1 ? 0xFFFFFFFFu / (unsigned)dim + 1u : 0u;
+        L.stride = (int)sd.in_stride[l];
+        L.pad = 0;
+        legs[k] = L;
+      }
+    }
+    wl[idx] = wv;
+  }
+  __syncwarp();
+  const int nenv = sd.nlegs - 1;
+  const char *tbase = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride);
+  auto row_ptr = [&](int r) {
+    const int rr = r < M ? r : 0;
+    const int s = rr / Dk, x = rr - s * Dk;
+    return tbase + 8 * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]);
+  };
+  auto build_table = [&](int c0) {
+#pragma unroll
+    for (int it = 0; it < LQW_CHUNK / 32; ++it) {
+      const int cc = lane + 32 * it;
+      LqcCol e;
+      e.ws = 0.0;
+      e.off = 0;
+      e.pad = 0;
+      if (c0 + cc < N) {
+        unsigned rem = (unsigned)(c0 + cc);
+        double wv = tsc;
+        unsigned off = 0;
+        for (int k = 0; k < nenv; ++k) {
+          const LqcLeg L = legs[k];
+          const unsigned qq = L.dim > 1 ? __umulhi(rem, L.magic) : rem;
+          const unsigned x = rem - qq * (unsigned)L.dim;
+          rem = qq;
+          off += x * (unsigned)L.stride;
+          wv *= wl[k * LQW_WL + x];
+        }
+        e.ws = wv;
+        e.off = (int)(off * 8u);
+      }
+      cols[cc] = e;
+    }
+  };
+  // fragments -> G (lower blocks), mirror, all by this warp
+  auto store_gram = [&](double (&acc)[NBLK][2]) {
+    int k = 0;
+#pragma unroll
+    for (int I = 0; I < MB; ++I)
+#pragma unroll
+      for (int J = 0; J <= I; ++J, ++k) {
+        double *d0 = G + (8 * I + g) * LD + 8 * J + 2 * t;
+        d0[0] = acc[k][0];
+        d0[1] = acc[k][1];
+      }
+    __syncwarp();
+    if (MB > 1) {
+      for (int idx = lane; idx < MP * MP; idx += 32) {
+        const int r = idx / MP, c = idx - r * MP;
+        if ((r >> 3) < (c >> 3)) G[r * LD + c] = G[c * LD + r];
+      }
+      __syncwarp();
+    }
+  };
+
+  // ------------------------------------------------------------------------------------------------ pass 1
+  const char *rowp1[MB];
+#pragma unroll
+  for (int I = 0; I < MB; ++I) rowp1[I] = row_ptr(8 * I + g);
+  double acc[NBLK][2];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) acc[k][0] = acc[k][1] = 0.0;
+  for (int c0 = 0; c0 < N; c0 += LQW_CHUNK) {
+    __syncwarp();
+    build_table(c0);
+    __syncwarp();
+    const int nks = (min(LQW_CHUNK, N - c0) + 3) >> 2;
+#pragma unroll 8
+    for (int ks = 0; ks < nks; ++ks) {
+      const LqcCol e = cols[4 * ks + t];
+      double v[MB];
+#pragma unroll
+      for (int I = 0; I < MB; ++I) v[I] = __ldg((const double *)(rowp1[I] + (unsigned)e.off));
+      const double w2 = e.ws * e.ws;
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        const double a = v[I] * w2;
+#pragma unroll
+        for (int J = 0; J <= I; ++J, ++k) lqc_dmma(acc[k][0], acc[k][1], a, v[J]);
+      }
+    }
+  }
+  store_gram(acc);
+  // ------------------------------------------------------------------------------------------------ L1, W1
+  bool ok;
+  {
+    double gr[MP], l1[MP], invd, x[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
+    ok = lqc_cholesky<MP>(gr, l1, invd, lane, M);
+    lqc_tri_inverse<MP>(l1, invd, x, lane);
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        W1s[r * LD + lane] = x[r];
+        L1s[lane * LD + r] = l1[r];
+      }
+    }
+  }
+  __syncwarp();
+  if (!ok) {
+    if (lane == 0) flags[w] = 1;
+    return;
+  }
+  // ------------------------------------------------------------------------------------------------ pass 2
+  double afr[MB][KS];
+#pragma unroll
+  for (int I = 0; I < MB; ++I)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int i = 8 * I + g, k = 4 * ks + t;
+      afr[I][ks] = (i < M && k < M) ? W1s[i * LD + k] : 0.0;
+    }
+  const char *rowp2[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) rowp2[ks] = row_ptr(4 * ks + t);
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) acc[k][0] = acc[k][1] = 0.0;
+  for (int c0 = 0; c0 < N; c0 += LQW_CHUNK) {
+    if (N > LQW_CHUNK) {
+      __syncwarp();
+      build_table(c0);
+      __syncwarp();
+    }
+    const int ntile = (min(LQW_CHUNK, N - c0) + 7) >> 3;
+#pragma unroll 2
+    for (int tl = 0; tl < ntile; ++tl) {
+      const unsigned off = (unsigned)cols[8 * tl + g].off;
+      double bv[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) bv[ks] = __ldg((const double *)(rowp2[ks] + off));
+      const double ws0 = cols[8 * tl + 2 * t].ws, ws1 = cols[8 * tl + 2 * t + 1].ws;
+      double q0[MB], q1[MB];
+#pragma unroll
+      for (int I = 0; I < MB; ++I) {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) lqc_dmma(d0, d1, afr[I][ks], bv[ks]);
+        q0[I] = d0 * ws0;
+        q1[I] = d1 * ws1;
+      }
+      int k = 0;
+#pragma unroll
+      for (int I = 0; I < MB; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J, ++k) {
+          lqc_dmma(acc[k][0], acc[k][1], q0[I], q0[J]);
+          lqc_dmma(acc[k][0], acc[k][1], q1[I], q1[J]);
+        }
+    }
+  }
+  store_gram(acc);
+  // ------------------------------------------------------------------------------------------------ L2, W2, products
+  {
+    double gr[MP], l2[MP], invd, x[MP];
+#pragma unroll
+    for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
+    ok = lqc_cholesky<MP>(gr, l2, invd, lane, M);
+    lqc_tri_inverse<MP>(l2, invd, x, lane);
+    __syncwarp();
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        W2s[r * LD + lane] = x[r];
+        G[lane * LD + r] = l2[r];  // L2 takes the Gram matrix's place
+      }
+    }
+  }
+  __syncwarp();
+  {
+    const double *L2s = G;
+    double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+    double *gL = small + (SM_L0 + side) * ldm * ldm;
+    double *gW = small + (SM_S0 + side) * ldm * ldm;
+    for (int idx = lane; idx < M * M; idx += 32) {
+      const int r = idx / M, j = idx - r * M;
+      double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+      int k = j;
+      for (; k + 1 <= r; k += 2) {
+        a0 = fma(L1s[r * LD + k], L2s[k * LD + j], a0);
+        a1 = fma(L1s[r * LD + k + 1], L2s[(k + 1) * LD + j], a1);
+        c0 = fma(W2s[r * LD + k], W1s[k * LD + j], c0);
+        c1 = fma(W2s[r * LD + k + 1], W1s[(k + 1) * LD + j], c1);
+      }
+      if (k <= r) {
+        a0 = fma(L1s[r * LD + k], L2s[k * LD + j], a0);
+        c0 = fma(W2s[r * LD + k], W1s[k * LD + j], c0);
+      }
+      gL[r * ldm + j] = a0 + a1;
+      gW[r * ldm + j] = c0 + c1;
+    }
+    if (lane == 0) flags[w] = ok ? 0 : 1;
+  }
+}
+
+// =================================================================================================================
 // K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one CTA of 4 warps per (item, side)
 // =================================================================================================================
 template <int MB>
@@ -503,6 +762,18 @@ cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flag
     cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
     if (s != cudaSuccess) return s;
     attr_done = true;
+  }
+  if (p.lqc_force_fallback != 2) {  // default: one warp per (item, side); 2 selects the two-warp-CTA kernel (A/B comparisons)
+    auto kw = lq_chol_warp_kernel<MB>;
+    static bool attr_w = false;
+    if (!attr_w) {
+      cudaError_t s = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
+      if (s != cudaSuccess) return s;
+      attr_w = true;
+    }
+    const int per_warp = lqw_smem_bytes_per_warp(MB);
+    kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
+    return cudaGetLastError();
   }
   kern<<<2 * n_items, LQC_THREADS, lqc_smem_bytes(MB), st>>>(p, flags);
   return cudaGetLastError();
