@@ -443,7 +443,7 @@ def run_gpu_arm(args):
                          "fp64_peak_tflops_measured": 36.2,
                          "note": "the edge update is FP64-pipe / latency bound, not HBM bound (DESIGN.md section 4): the SVD "
                                  "kernel moves almost no bytes and runs the FP64 pipe at ~46 %; the streaming K1 reads each site tensor "
-                                 "once from DRAM (its second pass hits L2) and K3 reads it again and writes it: 1.5x the algorithmic bytes"},
+                                 "twice and K3 reads it again and writes it: 2.0x the algorithmic bytes (1.7x with TNSU_LQ=cta, slower)"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cpu_edges} edge updates of one peps D=8 network, numpy/scipy oracle, 1 BLAS thread"},
             "clocks": clocks.summary(),
