@@ -690,6 +690,16 @@ __global__ void __launch_bounds__(RCC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
     rowout[I] = 8 * ((long long)s * sd.out_stride_phys + (long long)x * sd.out_stride[sd.bond_leg]);
   }
   const int nenv = sd.nlegs - 1;
+  // 32-byte accesses are possible when the innermost tensor axis is an environment leg whose dimension is a multiple of 4
+  // (four consecutive columns are then contiguous) and every other offset keeps the 32-byte alignment.  (The analogous
+  // row-vector fetch for an innermost bond leg was measured: no gain, 128 registers.)
+  bool vec_cols = false;
+  {
+    const int lin = sd.nlegs - 1;
+    if (sd.bond_leg != lin && lin >= 0 && sd.dims[lin] % 4 == 0 && sd.in_stride[lin] == 1 && sd.in_stride[sd.bond_leg] % 4 == 0 &&
+        sd.in_stride_phys % 4 == 0 && sd.point_stride % 4 == 0 && (((size_t)sd.base & 31) == 0))
+      vec_cols = true;
+  }
   double n2 = 0.0;
   for (int c0 = 0; c0 < N; c0 += LQC_CHUNK) {
     __syncthreads();
@@ -709,8 +719,49 @@ __global__ void __launch_bounds__(RCC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_k
     __syncthreads();
     const int ncols = min(LQC_CHUNK, N - c0);
     const int ntile = (ncols + 7) >> 3;
+    int tile0 = 0;
+    if (vec_cols) {
+      // 32 columns per warp trip with 32-byte accesses: lane (g, t) loads the columns 4g .. 4g+3 of its row with one
+      // LDG.256 per k-step; its j-th value is the B fragment of "tile j" = the columns {4 g' + j}.  The accumulators of the
+      // four tiles then hold, for this lane, the columns 8t + j and 8t + 4 + j: two contiguous groups of four -> one
+      // STG.256 each.  4x fewer load and store instructions than the tile-by-tile loop below.
+      const int ngrp = ncols >> 5;
+      for (int grp = warp; grp < ngrp; grp += RCC_THREADS / 32) {
+        const int cb = 32 * grp;
+        const unsigned off_in = (unsigned)coff[cb + 4 * g];
+        double bv[KS][4];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                       : "=d"(bv[ks][0]), "=d"(bv[ks][1]), "=d"(bv[ks][2]), "=d"(bv[ks][3])
+                       : "l"(rowin[ks] + off_in)
+                       : "memory");
+        const unsigned oa = (unsigned)coff[cb + 8 * t], ob = (unsigned)coff[cb + 8 * t + 4];
+#pragma unroll
+        for (int I = 0; I < MB; ++I) {
+          double da[4], db[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            da[j] = db[j] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) lqc_dmma(da[j], db[j], afr[I][ks], bv[ks][j]);
+          }
+          if (8 * I + g < Mout) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) n2 = fma(da[j], da[j], fma(db[j], db[j], n2));
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(tbase + rowout[I] + oa), "d"(da[0]), "d"(da[1]),
+                         "d"(da[2]), "d"(da[3])
+                         : "memory");
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(tbase + rowout[I] + ob), "d"(db[0]), "d"(db[1]),
+                         "d"(db[2]), "d"(db[3])
+                         : "memory");
+          }
+        }
+      }
+      tile0 = 4 * ngrp;  // the remaining (< 32) columns of the chunk go tile by tile
+    }
 #pragma unroll 2
-    for (int tl = warp; tl < ntile; tl += RCC_THREADS / 32) {
+    for (int tl = tile0 + warp; tl < ntile; tl += RCC_THREADS / 32) {
       // the whole (M x 8) input tile is in registers before the first element of the output tile is stored
       const unsigned off = (unsigned)coff[min(8 * tl + g, ncols - 1)];
       double bv[KS];
