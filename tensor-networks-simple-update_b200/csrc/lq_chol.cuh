@@ -479,20 +479,45 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
     __syncwarp();
     build_table(c0);
     __syncwarp();
+    // software pipeline: batches of PB k-steps, the loads of batch n+1 are in flight while the DMMAs of batch n issue
+    // (the table is zero-padded to the end of the chunk, so a partial last batch just adds zeros)
+    constexpr int PB = 8;
     const int nks = (min(LQW_CHUNK, N - c0) + 3) >> 2;
-#pragma unroll 8
-    for (int ks = 0; ks < nks; ++ks) {
-      const LqcCol e = cols[4 * ks + t];
-      double v[MB];
+    const int nb = (nks + PB - 1) / PB;
+    double v[PB][MB], w2[PB];
 #pragma unroll
-      for (int I = 0; I < MB; ++I) v[I] = __ldg((const double *)(rowp1[I] + (unsigned)e.off));
-      const double w2 = e.ws * e.ws;
-      int k = 0;
+    for (int u = 0; u < PB; ++u) {
+      const LqcCol e = cols[4 * u + t];
+      w2[u] = e.ws * e.ws;
 #pragma unroll
-      for (int I = 0; I < MB; ++I) {
-        const double a = v[I] * w2;
+      for (int I = 0; I < MB; ++I) v[u][I] = __ldg((const double *)(rowp1[I] + (unsigned)e.off));
+    }
+#pragma unroll 1
+    for (int bt = 0; bt < nb; ++bt) {
+      double vn[PB][MB], wn[PB];
+      const int nxt = (bt + 1 < nb) ? bt + 1 : bt;  // the last batch reloads itself (L1 hits)
 #pragma unroll
-        for (int J = 0; J <= I; ++J, ++k) lqc_dmma(acc[k][0], acc[k][1], a, v[J]);
+      for (int u = 0; u < PB; ++u) {
+        const LqcCol e = cols[4 * (nxt * PB + u) + t];
+        wn[u] = e.ws * e.ws;
+#pragma unroll
+        for (int I = 0; I < MB; ++I) vn[u][I] = __ldg((const double *)(rowp1[I] + (unsigned)e.off));
+      }
+#pragma unroll
+      for (int u = 0; u < PB; ++u) {
+        int k = 0;
+#pragma unroll
+        for (int I = 0; I < MB; ++I) {
+          const double a = v[u][I] * w2[u];
+#pragma unroll
+          for (int J = 0; J <= I; ++J, ++k) lqc_dmma(acc[k][0], acc[k][1], a, v[u][J]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PB; ++u) {
+        w2[u] = wn[u];
+#pragma unroll
+        for (int I = 0; I < MB; ++I) v[u][I] = vn[u][I];
       }
     }
   }
@@ -539,12 +564,21 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
       __syncwarp();
     }
     const int ntile = (min(LQW_CHUNK, N - c0) + 7) >> 3;
-#pragma unroll 2
-    for (int tl = 0; tl < ntile; ++tl) {
-      const unsigned off = (unsigned)cols[8 * tl + g].off;
-      double bv[KS];
+    // software pipeline over the tiles: the next tile's B fragments are in flight during this tile's DMMAs
+    double bv[KS];
+    {
+      const unsigned off0 = (unsigned)cols[g].off;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) bv[ks] = __ldg((const double *)(rowp2[ks] + off));
+      for (int ks = 0; ks < KS; ++ks) bv[ks] = __ldg((const double *)(rowp2[ks] + off0));
+    }
+#pragma unroll 1
+    for (int tl = 0; tl < ntile; ++tl) {
+      double bn[KS];
+      {
+        const unsigned offn = (unsigned)cols[8 * (tl + 1 < ntile ? tl + 1 : tl) + g].off;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) bn[ks] = __ldg((const double *)(rowp2[ks] + offn));
+      }
       const double ws0 = cols[8 * tl + 2 * t].ws, ws1 = cols[8 * tl + 2 * t + 1].ws;
       double q0[MB], q1[MB];
 #pragma unroll
@@ -563,6 +597,8 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
           lqc_dmma(acc[k][0], acc[k][1], q0[I], q0[J]);
           lqc_dmma(acc[k][0], acc[k][1], q1[I], q1[J]);
         }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) bv[ks] = bn[ks];
     }
   }
   store_gram(acc);
