@@ -441,6 +441,10 @@ def run_gpu_arm(args):
                          "avg_launch_ms": kern_ms / n_triples,
                          "ncu": {k: ncu.get(k) for k in ("kernel_time_us", "fp64_pipe_pct", "dram_throughput_pct", "source")},
                          "fp64_peak_tflops_measured": 36.2,
+                         "fp64_bound": {"fma_per_edge_update": 1.5e6 if not cplx else 6.0e6,
+                                        "cap_edge_updates_per_s": 36.2e12 / 2 / (1.5e6 if not cplx else 6.0e6),
+                                        "frac": (value / world) / (36.2e12 / 2 / (1.5e6 if not cplx else 6.0e6)),
+                                        "what": "FP64 FMA count of one edge update (DESIGN.md section 4) against the measured DFMA/DMMA rate: the bound that actually governs this path"},
                          "note": "the edge update is FP64-pipe / latency bound, not HBM bound (DESIGN.md section 4): the SVD "
                                  "kernel moves almost no bytes and runs the FP64 pipe at ~46 %; the streaming K1 reads each site tensor "
                                  "twice and K3 reads it again and writes it: 2.0x the algorithmic bytes (1.7x with TNSU_LQ=cta, slower)"},
