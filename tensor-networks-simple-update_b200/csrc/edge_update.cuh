@@ -79,6 +79,7 @@ struct EdgeLaunch {
   int svdw_precond;          // pivoted-QR preconditioner before the Jacobi iteration
   int svdw_ldt;              // leading dimension of its transpose buffer
   const int *lq_flags;       // streaming K1/K3 (lq_chol.cuh) ran first: per (item, side) 1 = the Householder kernels must process it, 0 = skip; nullptr = process all
+  int *lq_stats;             // [1] number of (item, side)s the Householder fallback had to factor (run-loop statistics) or nullptr
   int lqc_force_fallback;    // TNSU_LQ=fallback: the streaming kernel flags every (item, side) (tests of the fallback path)
   int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
@@ -483,6 +484,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   // one work item per CTA, except the persistent variants: STREAM, and the fallback behind the streaming
   // CholeskyQR2 kernel (lq_flags), where a small grid scans the flags and factors only the flagged (item, side)s
   const bool looped = STREAM || (!CLUSTER && p.lq_flags != nullptr);
+  int n_fallback = 0;  // flagged work items this CTA factored (lq_flags mode)
   for (int w = (int)(blockIdx.x / CL); w < n_work; w += (looped ? (int)gridDim.x : n_work)) {
   const int item = w >> 1;
   const int side = w & 1;
@@ -500,6 +502,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   }
 
   if (p.lq_flags != nullptr && p.lq_flags[w] == 0) continue;  // factored by the streaming CholeskyQR2 kernel already
+  ++n_fallback;
 
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
@@ -766,6 +769,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   }
   if (looped) __syncthreads();  // the shared matrices are reused by the next work item
   }  // work loop
+  if (p.lq_flags != nullptr && p.lq_stats != nullptr && lt == 0 && n_fallback > 0) atomicAdd(p.lq_stats, n_fallback);
 }
 
 // =============================================================================================

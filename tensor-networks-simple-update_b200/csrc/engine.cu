@@ -82,6 +82,10 @@ struct tnsu_engine {
   int force_ncols = 0;                    // TNSU_NCOLS=1|2: columns per thread in K1/K3 (experiments)
   bool svd_accumulate_v = false;          // TNSU_SVD_V=accumulate: warp SVD with the right rotations accumulated in registers (A/B comparisons)
   bool force_householder = false;         // TNSU_LQ=householder: no streaming CholeskyQR2 K1/K3 in front of the Householder kernels (A/B comparisons)
+  int *lq_stats = nullptr;                // device counter: (item, side)s factored by the Householder fallback since the last poll
+  long long lqc_attempted = 0;            // (item, side)s given to the streaming K1 since the last poll (host count)
+  long long lqc_suspend_until = -1;       // run loop: no streaming K1/K3 before this global sweep index (most items were flagged)
+  long long run_sweep_index = 0;          // global sweep index inside tnsu_run (for the suspension window)
   bool lqc_cta_kernel = false;            // TNSU_LQ=cta: two-warp-CTA streaming K1 instead of the one-warp-per-matrix kernel (A/B comparisons)
   bool lqc_force_fallback = false;        // TNSU_LQ=fallback: streaming kernel flags everything, the Householder fallback does all the work (tests)
   int *lq_flags = nullptr;                // [batch * max_level_size * 2] per (item, side): 1 = Householder kernels must process it
@@ -368,6 +372,8 @@ static int plan_sweep(tnsu_engine *e) {
     }
     if (e->lq_flags == nullptr) {
       cudaError_t st3 = cudaMalloc(&e->lq_flags, sizeof(int) * 2 * (size_t)e->batch * e->max_level_size);
+      if (st3 == cudaSuccess) st3 = cudaMalloc(&e->lq_stats, sizeof(int));
+      if (st3 == cudaSuccess) st3 = cudaMemsetAsync(e->lq_stats, 0, sizeof(int), e->stream);
       if (st3 != cudaSuccess) return fail(e, TNSU_E_CUDA, "flag allocation: %s", cudaGetErrorString(st3));
     }
   }
@@ -490,6 +496,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.svdw_precond = c.svdw_precond;
     p.svdw_ldt = c.svdw_ldt;
     p.lq_flags = nullptr;
+    p.lq_stats = nullptr;
     p.lqc_force_fallback = e->lqc_force_fallback ? 1 : (e->lqc_cta_kernel ? 2 : 0);
     p.svdw_accv = c.svdw_accv;
     p.svdw_tb_off = c.svdw_tb_off;
@@ -504,10 +511,12 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     if (e->profile) cudaEventRecord(e->pev[0], e->stream);
     int extra_launches = 0;
     if constexpr (sizeof(S) == 8) {
-      if (c.lqc && only_edge < 0) {
+      if (c.lqc && only_edge < 0 && e->run_sweep_index >= e->lqc_suspend_until) {
         // streaming CholeskyQR2 first; it flags the (item, side)s it cannot take and the Householder kernels below
         // then process exactly those (every other CTA of theirs returns at once)
         p.lq_flags = e->lq_flags;
+        p.lq_stats = e->lq_stats;
+        e->lqc_attempted += 2LL * n_items;
         st = launch_lq_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
         ++extra_launches;
       }
@@ -778,6 +787,7 @@ int tnsu_destroy(tnsu_engine *e) {
   for (void *p : e->ybuf) cudaFree(p);
   if (e->small) cudaFree(e->small);
   if (e->lq_flags) cudaFree(e->lq_flags);
+  if (e->lq_stats) cudaFree(e->lq_stats);
   for (int k = 0; k < 4; ++k)
     if (e->pev[k]) cudaEventDestroy(e->pev[k]);
   void *ptrs[] = {e->tnorm2, e->tticket, e->weights, e->tscale, e->edge_err, e->energy, e->gates, e->hams, e->op_buf, e->pair_val, e->cval,
@@ -1004,7 +1014,7 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   CKC(cudaMalloc(&e->r_conv, B * 4));
   CKC(cudaMalloc(&e->r_nchecks, B * 4));
   CKC(cudaMalloc(&e->r_nactive, 4));
-  CKC(cudaMallocHost(&e->h_nactive, 4));
+  CKC(cudaMallocHost(&e->h_nactive, 8));  // [active points, fallback count of the streaming K1]
   CKC(cudaMalloc(&e->dbg_sigma, 64 * 8));
   CKC(cudaMalloc(&e->dbg_info, 16 * 4));
   CKC(cudaEventCreate(&e->ev0));
@@ -1404,7 +1414,11 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int64_t graph_launches = 0;
+  e->lqc_suspend_until = -1;
+  e->lqc_attempted = 0;
+  if (e->lq_stats) CK(cudaMemsetAsync(e->lq_stats, 0, sizeof(int), e->stream));
   auto iteration = [&](long long it) -> int {
+    e->run_sweep_index = it;
     int rc = one_sweep(e, 0, e->r_slot, e->r_active);
     if (rc) return rc;
     if (it >= 2) {
@@ -1459,8 +1473,24 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
         break;
       }
       any = (*e->h_nactive > 0);
+      // the streaming K1/K3 is only worth its first pass while it keeps most of the bond matrices: when more than half of
+      // what it was given since the last poll came back flagged (converged states with small weights), the next 32 sweeps
+      // go straight to the Householder kernels, then it is tried again
+      if (e->lq_stats != nullptr && e->lqc_attempted > 0) {
+        ce = cudaMemcpyAsync(e->h_nactive + 1, e->lq_stats, 4, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->lq_stats, 0, sizeof(int), e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) {
+          rc_loop = fail(e, TNSU_E_CUDA, "run loop poll: %s", cudaGetErrorString(ce));
+          break;
+        }
+        if (2LL * e->h_nactive[1] > e->lqc_attempted) e->lqc_suspend_until = it + 1 + 32;
+        e->lqc_attempted = 0;
+      }
     }
   }
+  e->run_sweep_index = 0;
+  e->lqc_suspend_until = -1;
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   if (rc_loop != TNSU_OK) return rc_loop;

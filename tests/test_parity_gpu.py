@@ -234,33 +234,58 @@ def test_pair_rdm_kernels_agree(tnsu, monkeypatch, lattice, dim, d):
 def test_streaming_lq_flags_ill_conditioned_points(tnsu):
     """The streaming CholeskyQR2 K1/K3 (lq_chol.cuh) only keeps bond matrices whose Cholesky factor spans less than
     1e5 on its diagonal; the others are flagged and taken by the Householder kernels in the same level.  A batch that
-    mixes a well-conditioned point with one whose tensors have a 1e-8 slice on every leg (cond(P) ~ 1e8) must match
-    the oracle (reference simple_update.py:219-296) on both."""
+    mixes a well-conditioned point with two whose tensors have a 1e-8 slice on every leg (cond(P) ~ 1e8) must match
+    the oracle (reference simple_update.py:219-296) on all of them."""
     smat = tnsu.smc.infinite_structure_matrix_dict("peps")
     sx, sy, sz = tnsu.spin_operators(0.5)
     nets = []
-    for k in range(2):
+    for k in range(3):
         np.random.seed(300 + k)
         tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
-        if k == 1:
+        if k >= 1:
             scale = np.ones(8)
             scale[7] = 1e-8
             tn.tensors = [t * scale[None, :, None, None, None] * scale[None, None, :, None, None] *
                           scale[None, None, None, :, None] * scale[None, None, None, None, :] for t in tn.tensors]
         nets.append(tn)
     ref = [tn.copy() for tn in nets]
-    batch = tnsu.SimpleUpdateBatch(nets, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=8, max_iterations=2,
+    # (the 1e-8 slices are flagged in the first sweep only: one update turns them into small WEIGHTS, which do not hurt)
+    batch = tnsu.SimpleUpdateBatch(nets, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=8, max_iterations=7,
                                    convergence_error=1e-30)
     batch.run()
     energies = batch.energy_per_site()
     model = orc.Model([1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [])
-    for k in range(2):
+    for k in range(3):
         t, w = [np.array(x) for x in ref[k].tensors], [np.array(x) for x in ref[k].weights]
-        orc.run(t, w, smat, model, [0.05], 8, 2, 1e-30)
+        orc.run(t, w, smat, model, [0.05], 8, 7, 1e-30)
         for a, b in zip(w, nets[k].weights):
             assert np.abs(a - b).max() < TOL_W
         e_ref = orc.energy_per_site(t, w, smat, model)
         assert abs(e_ref - energies[k]) < TOL_E * max(1.0, abs(e_ref))
+
+
+def test_streaming_lq_is_suspended_when_mostly_flagged(tnsu, monkeypatch):
+    """run(): when more than half of the bond matrices given to the streaming K1 since the last poll came back flagged,
+    the next 32 sweeps go straight to the Householder kernels (engine.cu: lqc_suspend_until).  With TNSU_LQ=fallback
+    everything is flagged: 7 sweeps = 4 with 5 launches per level + 3 with 3 (+ energy and state-machine launches), and
+    the results equal the default run."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    out = []
+    for env in ("", "fallback"):
+        monkeypatch.delenv("TNSU_LQ", raising=False)
+        if env:
+            monkeypatch.setenv("TNSU_LQ", env)
+        np.random.seed(77)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+        batch = tnsu.SimpleUpdateBatch([tn], [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=8, max_iterations=7,
+                                       convergence_error=1e-30)
+        batch.run()
+        out.append(([np.array(w) for w in tn.weights], batch.engine.launch_count))
+    # 6 levels per sweep x 5 launches, + 2 energy launches from the third sweep on, + 1 state-machine launch per sweep
+    assert out[0][1] == 7 * 30 + 5 * 2 + 7
+    assert out[1][1] == 4 * 30 + 3 * 18 + 5 * 2 + 7
+    assert max(np.abs(a - b).max() for a, b in zip(out[0][0], out[1][0])) < 1e-12
 
 
 def test_batch_matches_single_and_oracle(tnsu):
