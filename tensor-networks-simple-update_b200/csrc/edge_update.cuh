@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   const bool looped = STREAM || (!CLUSTER && p.lq_flags != nullptr);
   int n_fallback = 0;  // flagged work items this CTA factored (lq_flags mode)
   for (int w = (int)(blockIdx.x / CL); w < n_work; w += (looped ? (int)gridDim.x : n_work)) {
+  if (!CLUSTER && p.lq_flags != nullptr && p.lq_flags[w] == 0) continue;  // taken by the streaming kernel: one load per scanned item
   const int item = w >> 1;
   const int side = w & 1;
   const int b = item / p.n_level_edges;

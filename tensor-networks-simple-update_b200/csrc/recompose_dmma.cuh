@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(RCD_THREADS, (MBO * KB <= 4) ? 4 : 3) recompos
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int KS = 2 * KB;  // k-steps of 4
   const int CL = p.cluster;
+  if (p.lq_flags != nullptr && p.lq_flags[blockIdx.x / CL] == 0) return;  // recomposed by recompose_chol_kernel (checked first: most CTAs end here)
   const int rank = (int)(blockIdx.x % CL);
   const int item = (int)(blockIdx.x / CL) >> 1;
   const int side = (int)(blockIdx.x / CL) & 1;
