@@ -193,8 +193,9 @@ __global__ void __launch_bounds__(RDM_THREADS) pair_rdm_kernel(const PairRdmLaun
 // CTAs of one point are adjacent in the grid, so a site tensor shared by several edges is read from
 // DRAM once and from L2 afterwards.
 // ---------------------------------------------------------------------------------------------
-#define PG_THREADS 256
-#define PG_CHUNK 512  // columns per side and pass
+#define PG_WPS 1      // warps per side: one warp owns a whole Gram matrix (no partial sums, one barrier per chunk)
+#define PG_THREADS (64 * PG_WPS)
+#define PG_CHUNK 128  // columns per side and pass
 #define PG_UNROLL 4   // k-steps in flight per warp
 #define PG_WL 32      // leading dimension of the per-leg weight table (D <= 16 whenever d*D <= 32)
 
@@ -232,7 +233,7 @@ static inline int pair_dmma_smem_bytes(int MB, int d4) {
 }
 
 template <int MB>
-__global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_kernel(const PairRdmLaunch<double> p) {
+__global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THREADS)) pair_rdm_dmma_kernel(const PairRdmLaunch<double> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB;
   constexpr int NBLK = MB * (MB + 1) / 2;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   }
   const EdgeDesc &ed = p.descs[ek];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int side = warp >> 2, q = warp & 3, g = lane >> 2, t = lane & 3;
+  const int side = warp / PG_WPS, q = warp % PG_WPS, g = lane >> 2, t = lane & 3;
   const int d = ed.d, Dk = ed.Dk, M = d * Dk;
 
   PgCol *cols = (PgCol *)smem_raw;                           // [2][PG_CHUNK]
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   {
     const char *tb = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride);
     const long long bytes = (long long)M * sd.N * 8;
-    for (long long o = (long long)(tid & 127) * 128; o < bytes; o += 128 * 128)
+    for (long long o = (long long)(tid % (32 * PG_WPS)) * 128; o < bytes; o += 32 * PG_WPS * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + o));
   }
   // rows past M are clamped to row 0: their Gram entries are computed and never read
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   const int nenv0 = ed.s[0].nlegs - 1, nenv1 = ed.s[1].nlegs - 1;
   const int N0 = ed.s[0].N, N1 = ed.s[1].N;
   const int Nmax = max(N0, N1);
-  constexpr int KSTEP_GROUP = 4 * PG_UNROLL;  // k-steps per trip of the four warps of a side
+  constexpr int KSTEP_GROUP = PG_WPS * PG_UNROLL;  // k-steps per trip of the warps of a side
   for (int c0 = 0; c0 < Nmax; c0 += PG_CHUNK) {
     __syncthreads();  // legs / wsq ready, previous chunk consumed
     // each thread decodes 2 * PG_CHUNK / PG_THREADS entries, unrolled: the weight products are dependent FP64 chains
@@ -378,10 +379,10 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
         for (int I = 0; I < MB; ++I) pg_ldvec<4>(rowp[I] + off, v[I]);
       }
 #pragma unroll 1
-      for (int gr = q; gr < ngr; gr += 4) {
+      for (int gr = q; gr < ngr; gr += PG_WPS) {
         double vn[MB][4], wn[4];
         {
-          const PgCol *e = cg + 16 * (gr + 4 < ngr ? gr + 4 : gr);
+          const PgCol *e = cg + 16 * (gr + PG_WPS < ngr ? gr + PG_WPS : gr);
 #pragma unroll
           for (int j = 0; j < 4; ++j) wn[j] = e[j].w;
           const unsigned off = (unsigned)e[0].off;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
         double v[PG_UNROLL][MB], w[PG_UNROLL];
 #pragma unroll
         for (int u = 0; u < PG_UNROLL; ++u) {
-          const PgCol e = cl[4 * (q + 4 * u)];
+          const PgCol e = cl[4 * (q + PG_WPS * u)];
           w[u] = e.w;
           pg_ldvec<MB>(rowp[0] + (unsigned)e.off, v[u]);
         }
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
           const int ksn = ks0 + KSTEP_GROUP < nks_pad ? ks0 + KSTEP_GROUP : ks0;
 #pragma unroll
           for (int u = 0; u < PG_UNROLL; ++u) {
-            const PgCol e = cl[4 * (ksn + 4 * u)];
+            const PgCol e = cl[4 * (ksn + PG_WPS * u)];
             wn[u] = e.w;
             pg_ldvec<MB>(rowp[0] + (unsigned)e.off, vn[u]);
           }
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
       double v[PG_UNROLL][MB], w[PG_UNROLL];
 #pragma unroll
       for (int u = 0; u < PG_UNROLL; ++u) {
-        const PgCol e = cl[4 * (q + 4 * u)];
+        const PgCol e = cl[4 * (q + PG_WPS * u)];
         w[u] = e.w;
 #pragma unroll
         for (int I = 0; I < MB; ++I) v[u][I] = __ldg((const double *)(rowp[I] + (unsigned)e.off));
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
         const int ksn = ks0 + KSTEP_GROUP < nks_pad ? ks0 + KSTEP_GROUP : ks0;  // last trip reloads itself (L1 hit)
 #pragma unroll
         for (int u = 0; u < PG_UNROLL; ++u) {
-          const PgCol e = cl[4 * (ksn + 4 * u)];
+          const PgCol e = cl[4 * (ksn + PG_WPS * u)];
           wn[u] = e.w;
 #pragma unroll
           for (int I = 0; I < MB; ++I) vn[u][I] = __ldg((const double *)(rowp[I] + (unsigned)e.off));
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(PG_THREADS, MB <= 2 ? 4 : 2) pair_rdm_dmma_ker
   int *modes = (int *)(red + 1);  // [2] fetch mode of each side (for the symmetric fill below)
   if (lane == 0 && q == 0) modes[side] = mode;
   double *gs = gram + side * MP * MP;
-  for (int wv = 0; wv < 4; ++wv) {
+  for (int wv = 0; wv < PG_WPS; ++wv) {
     __syncthreads();
     if (q == wv) {
       int k = 0;
