@@ -23,7 +23,7 @@
 #include "edge_update.cuh"
 
 #define LQC_THREADS 64   // K1c: two warps per (item, side) — the Cholesky phases keep one of them idle, not three
-#define RCC_THREADS 128  // K3c
+#define RCC_THREADS 32   // K3c: one warp per (item, side) too (4 warps: 4.98 ms, 2 warps: 4.48 ms, 1 warp: 4.40 ms per sweep)
 #define LQC_CHUNK 512
 #define LQC_WL 32
 
@@ -646,10 +646,10 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
 }
 
 // =================================================================================================================
-// K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one CTA of 4 warps per (item, side)
+// K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one warp (= one CTA) per (item, side)
 // =================================================================================================================
 template <int MB>
-__global__ void __launch_bounds__(RCC_THREADS, MB <= 2 ? 4 : 2) recompose_chol_kernel(const EdgeLaunch<double> p,
+__global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_THREADS)) recompose_chol_kernel(const EdgeLaunch<double> p,
                                                                                        const int *flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, KS = 2 * MB;
