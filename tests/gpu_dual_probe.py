@@ -5,7 +5,7 @@ sys.path.insert(0, __file__.rsplit("/", 2)[0])
 import bench  # noqa: E402
 import tnsu_b200 as tnsu  # noqa: E402
 
-B = 8192
+B = 9472
 K = 10
 smat, tensors, weights = bench.seeded_networks(B)
 ham, gate = bench.afh_operators()
@@ -34,7 +34,7 @@ one = make(0, B)
 t1 = timed([one]); t1 = timed([one])
 print(f"1 engine  x {B}: {1e3*t1/K:.2f} ms/sweep  {B*8*K/t1/1e6:.3f} M edge-updates/s")
 one.close()
-for parts in (2, 3, 4):
+for parts in (2, 4):
     bounds = np.linspace(0, B, parts + 1).astype(int)
     engs = [make(int(bounds[i]), int(bounds[i+1])) for i in range(parts)]
     t = timed(engs); t = timed(engs)
