@@ -46,7 +46,7 @@ enum {
 };
 
 /* ABI version of this header; tnsu_abi_version() must return the same number. */
-#define TNSU_ABI_VERSION 1
+#define TNSU_ABI_VERSION 2
 int tnsu_abi_version(void);
 
 /* Text of the last error on this handle (or of the last failed tnsu_create when e == NULL). */
@@ -73,7 +73,10 @@ int tnsu_num_levels(const tnsu_engine *e);                  /* dependency levels
 int tnsu_edge_levels(const tnsu_engine *e, int32_t *level_out /* [m] */);
 
 /* State upload / download.  `host` holds `batch` tensors back to back, each in the engine dtype
- * (float64 or complex128) with the CURRENT shape.  `pinned` != 0 promises page-locked memory.
+ * (float64 or complex128) with the CURRENT shape (pageable or page-locked memory; the copy is complete on return).
+ * The download entry points synchronise, and — like tnsu_sweep_error, tnsu_synchronize and tnsu_run — return
+ * TNSU_E_NONFINITE (once) when an update since the last check met NaN / Inf: the reference raises ValueError from
+ * scipy's finite check inside simple_update at that point (simple_update.py:243-250, :404).
  * Replaces: the list entries TensorNetwork.tensors[t] / .weights[e] (tensor_network.py:119-120). */
 int tnsu_set_tensor(tnsu_engine *e, int t, const void *host, int64_t elems_per_point);
 int tnsu_get_tensor(tnsu_engine *e, int t, void *host, int64_t elems_per_point);
@@ -111,10 +114,11 @@ int tnsu_expectation_per_site(tnsu_engine *e, const void *op_c128, void *out_c12
 /* Whole SimpleUpdate.run() for every point (simple_update.py:107-194): slots 0..n_dts-1 are the dt
  * schedule (gates must be set for each), `is_last_value[s]` != 0 where dts[s] == dts[-1] (the
  * reference compares VALUES, :176).  Per-point outputs; logs are [batch][log_cap] with
- * n_checks[b] valid entries (one per convergence check, i.e. every 2nd sweep of a dt, :132). */
+ * n_checks[b] valid entries (one per convergence check, i.e. every 2nd sweep of a dt, :132); final_slot[b] is the
+ * last time-step slot the point entered (the reference leaves self.dt = dts[final_slot], :119). */
 int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_iterations, double tol,
              int log_cap, int32_t *n_checks, double *log_error, double *log_energy, int32_t *log_slot,
-             int32_t *log_step, int32_t *converged, int32_t *total_sweeps);
+             int32_t *log_step, int32_t *converged, int32_t *total_sweeps, int32_t *final_slot);
 
 /* Timing / stream plumbing for benchmarks. */
 void *tnsu_stream(tnsu_engine *e);
@@ -125,16 +129,13 @@ int64_t tnsu_launch_count(const tnsu_engine *e);
  * the most recent tnsu_sweep call, and their count. */
 int tnsu_last_sweep_kernel_ms(tnsu_engine *e, double *total_ms, int32_t *n_launches);
 
-/* One sweep with CUDA events between the kernel classes (synchronises after every launch: for profiling
- * only).  ms_out[3] = total device time of {K1 absorb+LQ, K2 theta+SVD, K3 recompose+store} launches. */
-int tnsu_profile_sweep(tnsu_engine *e, int slot, double *ms_out);
-
-/* Debug: run ONE edge update of point `point` and return the kernel's intermediates
- * (L_i, L_j as [M][K] row-major, theta singular values) for step-by-step comparison with
- * oracle/device_model.py.  Buffers are complex128 / float64 with capacity 64*64 / 64. */
-int tnsu_debug_edge(tnsu_engine *e, int slot, int edge, int point, void *l_i_c128, void *l_j_c128,
-                    double *sigma,
-                    int32_t *info /* [16]: M_i K_i M_j K_j n_i n_j D_new svd_sweeps, then K2 cycle counts theta/jacobi/extract */);
+/* Cumulative counters of this handle (synchronises): out[0] kernels launched, out[1] (item, side) bond matrices given to
+ * the streaming CholeskyQR2 reduction, out[2] of those flagged ill-conditioned and re-done by the Householder kernels,
+ * out[3] Jacobi iterations that hit their sweep limit (the SVD is then only as converged as the limit allowed; the
+ * reference's LAPACK driver would raise LinAlgError), out[4] non-finite events reported, out[5] tnsu_run calls served by
+ * the on-chip persistent kernel.  At most n_out entries are written. */
+#define TNSU_N_STATS 6
+int tnsu_stats(tnsu_engine *e, int64_t *out, int n_out);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,12 @@ def sweep_case(name):
         store[f"site_rdm_{t}"] = r_ref
     op1 = case["s_i"][-1]
     store["expect1"] = np.array(sim.expectation_per_site(op1))
+    # two-site observable family (simple_update.py:605-613, :639-649) and the one-site expectation (:595-603)
+    op2 = np.reshape(np.kron(case["s_i"][-1], case["s_j"][0]), (d, d, d, d))
+    store["pair_expect_per_site"] = np.array(sim.pair_expectation_per_site(op2))
+    store["pair_expect_edge"] = np.array([sim.tensor_pair_expectation(e, op2) for e in rdm_edges])
+    store["site_expect_0"] = np.array(sim.tensor_expectation(0, op1))
+    dev_e = max(dev_e, abs(float(store["pair_expect_per_site"]) - orc.pair_expectation_per_site(o_t, o_w, smat, op2)))
     store["energies"] = np.array(energies)
     store["abs_tensor_0"] = np.abs(tn.tensors[0])
     store["oracle_dev_weights"] = np.array(dev_w)
@@ -99,6 +105,8 @@ def run_case(name):
     np.random.seed(case["seed"])
     tn = RefTensorNetwork(structure_matrix=smat, tensors=None, weights=None, spin_dim=d,
                           virtual_dim=case["virtual_dim"])
+    if case.get("complex_init"):
+        tn.tensors = [t + 1j * np.random.normal(size=t.shape) for t in tn.tensors]
     sim = ref_su.SimpleUpdate(
         tn, case["j_ij"], case["h_k"], case["s_i"], case["s_j"], case["s_k"], case["dts"],
         d_max=case["d_max"], max_iterations=case["max_iterations"], convergence_error=case["tol"],
@@ -110,6 +118,8 @@ def run_case(name):
 
     np.random.seed(case["seed"])
     o_t, o_w = orc.random_network(smat, d, case["virtual_dim"])
+    if case.get("complex_init"):
+        o_t = [t + 1j * np.random.normal(size=t.shape) for t in o_t]
     model = orc.Model(case["j_ij"], case["h_k"], case["s_i"], case["s_j"], case["s_k"], case["hamiltonian"])
     log = orc.run(o_t, o_w, smat, model, case["dts"], case["d_max"], case["max_iterations"], case["tol"])
     e_orc = orc.energy_per_site(o_t, o_w, smat, model)
@@ -125,6 +135,7 @@ def run_case(name):
         "oracle_dev_energy": np.array(abs(e_ref - e_orc)),
         "oracle_dev_checks": np.array(abs(len(log["error"]) - len(sim.logger["error"]))),
         "oracle_dev_weights": np.array(max(np.abs(a - b).max() for a, b in zip(tn.weights, o_w))),
+        "min_weight": np.array(min(float(np.min(w)) for w in tn.weights)),
     }
     _pack_list("weights", tn.weights, store)
     np.savez_compressed(os.path.join(OUT, f"run_{name}.npz"), **store)
@@ -154,6 +165,11 @@ def pickled_state():
     _pack_list("tensors", tn.tensors, store)
     _pack_list("weights", tn.weights, store)
     np.savez_compressed(os.path.join(OUT, "pkl_afh_10x10_obc_D4.npz"), **store)
+    # the shipped pickle itself (data, 778 kB): the input of the load_network known-answer test on the GPU box
+    import shutil
+    os.makedirs(os.path.join(OUT, "networks"), exist_ok=True)
+    shutil.copyfile("/root/reference/src/tnsu/networks/AFH_10x10_obc_D_4.pkl",
+                    os.path.join(OUT, "networks", "AFH_10x10_obc_D_4.pkl"))
     return {"energy": e_ref, "dev_e": abs(e_ref - e_orc), "vs_known": abs(e_ref + 0.5616206254235453)}
 
 
@@ -175,9 +191,13 @@ def smat_fixtures():
 def main():
     os.makedirs(OUT, exist_ok=True)
     manifest = {"numpy": np.__version__, "scipy": __import__("scipy").__version__, "cases": {}}
-    smat_fixtures()
-    manifest["cases"]["pkl_afh_10x10_obc_D4"] = pickled_state()
-    print("pkl", manifest["cases"]["pkl_afh_10x10_obc_D4"])
+    mpath = os.path.join(OUT, "manifest.json")
+    if len(sys.argv) > 1 and os.path.exists(mpath):  # a subset: keep the other cases' entries
+        manifest["cases"] = json.load(open(mpath))["cases"]
+    else:
+        smat_fixtures()
+        manifest["cases"]["pkl_afh_10x10_obc_D4"] = pickled_state()
+        print("pkl", manifest["cases"]["pkl_afh_10x10_obc_D4"])
     for name, case in CASES.items():
         kind = case["kind"]
         if len(sys.argv) > 1 and name not in sys.argv[1:]:

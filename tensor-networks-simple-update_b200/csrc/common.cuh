@@ -10,6 +10,26 @@
 #define TNSU_MAX_SVD 64   // max rows/cols of theta
 #define TNSU_MAX_WARPS 16 // max warps per side group
 
+#define TNSU_SMEM_OPT_IN (227 * 1024)
+
+// Opt a kernel in to the full dynamic shared memory of the device the caller is on.  The attribute is per DEVICE, an
+// engine may sit on any of them and several host threads drive engines at once: one locked (kernel, device) set.
+#include <mutex>
+#include <set>
+#include <utility>
+inline cudaError_t tnsu_opt_in_smem(const void *kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;
+  int dev = 0;
+  cudaError_t s = cudaGetDevice(&dev);
+  if (s != cudaSuccess) return s;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return cudaSuccess;
+  s = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_OPT_IN);
+  if (s == cudaSuccess) done.insert({kernel, dev});
+  return s;
+}
+
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
 

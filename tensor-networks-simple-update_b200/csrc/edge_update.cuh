@@ -84,6 +84,9 @@ struct EdgeLaunch {
   int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;
+  int svd_max_sweeps;        // Jacobi sweep limit (60 for the warp kernel, 40 for the shared-memory one; TNSU_SVD_MAX_SWEEPS overrides: tests)
+  int *status;               // [2] device failure counters: [0] != 0 once a theta had no finite positive singular-value sum
+                             // (NaN / Inf in the state), [1] Jacobi iterations that hit their sweep limit
   // debug dump (tnsu_debug_edge)
   double *dbg_sigma;
   int *dbg_info;
@@ -803,7 +806,7 @@ DEV void jacobi_rotation(double al, double be, cplx ga, double &c, cplx &sp, cpl
 
 // A is nr x nc column-major (nr >= nc), V nc x nc.  RPL = rows of A per lane, CPL = rows of V per lane.
 template <typename S, int RPL, int CPL>
-__device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile int *flag, int tid, int nthr) {
+__device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile int *flag, int tid, int nthr, int max_sweeps) {
   for (int idx = tid; idx < nc * nc; idx += nthr) {
     int col = idx / nc, row = idx - col * nc;
     V[col * ldv + row] = from_real<S>(row == col ? 1.0 : 0.0);
@@ -818,7 +821,7 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
   const double tol2 = 2.25e-30;  // (1.5e-15)^2
   int sweeps = 0;
   __syncthreads();
-  for (; sweeps < 40; ++sweeps) {
+  for (; sweeps < max_sweeps; ++sweeps) {
     if (tid == 0) *flag = 0;
     __syncthreads();
     for (int r = 0; r < nm1; ++r) {
@@ -895,13 +898,10 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
       }
       __syncthreads();
     }
-    if (*flag == 0) {
-      ++sweeps;
-      break;
-    }
+    if (*flag == 0) return sweeps + 1;
     __syncthreads();  // everyone has read the flag before the next sweep resets it
   }
-  return sweeps;
+  return 99;  // sweep limit reached without a rotation-free sweep
 }
 
 // resident CTAs per SM the register allocator should aim for: the Jacobi phase is latency bound, so occupancy
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
       }
   }
   long long clk1 = clock64();
-  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr);
+  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40));
   long long clk2 = clock64();
 
   // singular values, descending order
@@ -1014,6 +1014,8 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
   if (tid == 0) {
     double tot = 0.0;
     for (int x = 0; x < Dnew; ++x) tot += sig[order[x]];
+    if (!(tot > 0.0 && tot < 1e300)) atomicOr(p.status, 1);
+    if (svd_sweeps == 99) atomicAdd(p.status + 1, 1);
     double err2 = 0.0;
     for (int x = 0; x < Dnew; ++x) {
       const double ln = sig[order[x]] / tot;
@@ -1200,12 +1202,7 @@ template <int MM, int NC>
 cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
   if (p.lq_stream_grid > 0) {
     auto kern = lq_rolled_kernel<MM, NC, true, false>;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-      if (s != cudaSuccess) return s;
-      attr_done = true;
-    }
+    if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
     const int grid = (2 * n_items < p.lq_stream_grid) ? 2 * n_items : p.lq_stream_grid;
     kern<<<grid, p.nt, p.smem_lq, st>>>(p);
     return cudaGetLastError();
@@ -1213,12 +1210,7 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
   if (p.cluster > 1) {
     // one thread-block cluster per (item, side): the CTAs exchange their partial Gram rows through DSMEM
     auto kernc = lq_rolled_kernel<MM, NC, false, true>;
-    static bool attr_done_c = false;
-    if (!attr_done_c) {
-      cudaError_t s = cudaFuncSetAttribute(kernc, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-      if (s != cudaSuccess) return s;
-      attr_done_c = true;
-    }
+    if (cudaError_t s = tnsu_opt_in_smem((const void *)kernc); s != cudaSuccess) return s;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * n_items * p.cluster);
     cfg.blockDim = dim3(p.nt);
@@ -1234,12 +1226,7 @@ cudaError_t launch_lq_rolled(const EdgeLaunch<double> &p, int n_items, cudaStrea
     return cudaLaunchKernelEx(&cfg, kernc, p);
   }
   auto kern = lq_rolled_kernel<MM, NC, false, false>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   const int grid = (p.lq_flags != nullptr && 2 * n_items > 1184) ? 1184 : 2 * n_items;  // fallback scan: 8 CTAs per SM
   kern<<<grid, p.nt, p.smem_lq, st>>>(p);
   return cudaGetLastError();
@@ -1251,12 +1238,7 @@ cudaError_t launch_lq_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t 
     if (p.lq_rolled) return launch_lq_rolled<MM, NC>(p, n_items, st);
   }
   auto kern = lq_kernel<S, MM, NC>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<2 * n_items, p.nt, p.smem_lq, st>>>(p);
   return cudaGetLastError();
 }
@@ -1264,12 +1246,7 @@ cudaError_t launch_lq_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t 
 template <typename S, int MM, int NC>
 cudaError_t launch_rc_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
   auto kern = recompose_kernel<S, MM, NC>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<2 * n_items * p.cluster, p.nt, p.smem_rc, st>>>(p);
   return cudaGetLastError();
 }
@@ -1277,12 +1254,7 @@ cudaError_t launch_rc_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t 
 template <typename S, int RPL>
 cudaError_t launch_svd_rpl(const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
   auto kern = svd_kernel<S, RPL>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<n_items, SVD_THREADS, p.smem_svd, st>>>(p);
   return cudaGetLastError();
 }

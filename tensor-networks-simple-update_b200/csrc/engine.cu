@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/tnsu_b200.h"
+#include "../../include/tnsu_b200_debug.h"
 #include "edge_update.cuh"
 #include "rdm.cuh"
 
@@ -103,6 +104,12 @@ struct tnsu_engine {
   double *r_log_err = nullptr, *r_log_energy = nullptr;
   int r_log_cap = 0;
   int *h_nactive = nullptr;  // pinned
+  // failure counters (edge_update.cuh: EdgeLaunch::status) and cumulative statistics (tnsu_stats)
+  int *d_status = nullptr;   // [2] device
+  int *h_status = nullptr;   // [2] pinned
+  int svd_max_sweeps = 1 << 20;  // TNSU_SVD_MAX_SWEEPS: lowers the kernels' Jacobi sweep limit (tests of the non-convergence counter)
+  long long fused_runs = 0;  // tnsu_run calls served by the on-chip persistent kernel (run_fused.cuh)
+  long long lqc_attempted_total = 0, lqc_flagged_total = 0, svd_unconverged_total = 0, nonfinite_events = 0;
   // debug buffers
   double *dbg_sigma = nullptr;
   int *dbg_info = nullptr;
@@ -133,7 +140,43 @@ static int fail(tnsu_engine *e, int code, const char *fmt, ...) {
     if (_s != cudaSuccess) return fail(e, TNSU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_s)); \
   } while (0)
 
-static int align16(int x) { return (x + 15) & ~15; }
+// Every ABI entry point runs on the engine's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&prev);
+    if (status != cudaSuccess) {
+      prev = -1;
+      return;
+    }
+    if (prev != device) status = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(e)                   \
+  DeviceGuard _guard((e)->device);     \
+  CK(_guard.status)
+
+// Read the device failure counters (synchronises the stream).  A non-finite bond is reported ONCE, as the reference
+// raises once from scipy's check_finite inside simple_update (simple_update.py:243-250, :404).
+static int poll_status(tnsu_engine *e) {
+  CK(cudaMemcpyAsync(e->h_status, e->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const int bad = e->h_status[0], slow = e->h_status[1];
+  if (bad || slow) CK(cudaMemsetAsync(e->d_status, 0, 2 * sizeof(int), e->stream));
+  e->svd_unconverged_total += slow;
+  if (bad) {
+    ++e->nonfinite_events;
+    return fail(e, TNSU_E_NONFINITE,
+                "a bond update produced singular values that are not finite and positive: NaN / Inf in the tensors, "
+                "weights or gates");
+  }
+  return TNSU_OK;
+}
 
 static int max_threads(bool cplx_, int mm, int nc) {
   int doubles = mm * nc * (cplx_ ? 2 : 1);
@@ -500,6 +543,8 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.lqc_force_fallback = e->lqc_force_fallback ? 1 : (e->lqc_cta_kernel ? 2 : 0);
     p.svdw_accv = c.svdw_accv;
     p.svdw_tb_off = c.svdw_tb_off;
+    p.status = e->d_status;
+    p.svd_max_sweeps = e->svd_max_sweeps;
     p.dbg_info = nullptr;
     if (dbg_point >= 0) {
       p.dbg_sigma = e->dbg_sigma;
@@ -517,6 +562,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
         p.lq_flags = e->lq_flags;
         p.lq_stats = e->lq_stats;
         e->lqc_attempted += 2LL * n_items;
+        e->lqc_attempted_total += 2LL * n_items;
         st = launch_lq_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
         ++extra_launches;
       }
@@ -615,11 +661,7 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
   }
   int smem = pair_smem_bytes(e, maxM);
   if (smem > SMEM_LIMIT) return fail(e, TNSU_E_UNSUPPORTED, "pair RDM needs %d bytes of shared memory", smem);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CK(cudaFuncSetAttribute(pair_rdm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_done = true;
-  }
+  CK(tnsu_opt_in_smem((const void *)pair_rdm_kernel<S>));
   pair_rdm_kernel<S><<<e->batch * n_list, RDM_THREADS, smem, e->stream>>>(p);
   CK(cudaGetLastError());
   e->launches++;
@@ -781,7 +823,7 @@ int tnsu_schedule_levels(int n, int m, const int64_t *smat, int32_t *level_out) 
 
 int tnsu_destroy(tnsu_engine *e) {
   if (!e) return TNSU_OK;
-  cudaSetDevice(e->device);
+  DeviceGuard guard(e->device);
   cudaStreamSynchronize(e->stream);
   for (void *p : e->tens) cudaFree(p);
   for (void *p : e->ybuf) cudaFree(p);
@@ -798,6 +840,8 @@ int tnsu_destroy(tnsu_engine *e) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
+  if (e->h_status) cudaFreeHost(e->h_status);
+  if (e->d_status) cudaFree(e->d_status);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -875,6 +919,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     e->lqc_force_fallback = env && std::string(env) == "fallback";
     e->lqc_cta_kernel = env && std::string(env) == "cta";
+    env = getenv("TNSU_SVD_MAX_SWEEPS");
+    if (env && atoi(env) > 0) e->svd_max_sweeps = atoi(env);
     env = getenv("TNSU_RC");
     e->force_simple_rc = env && std::string(env) == "simple";
     env = getenv("TNSU_RDM");
@@ -958,7 +1004,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     }                                                                                            \
   } while (0)
 
-  CKC(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CKC(guard.status);
   CKC(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (stream) {
     e->stream = (cudaStream_t)stream;
@@ -1015,6 +1062,9 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
   CKC(cudaMalloc(&e->r_nchecks, B * 4));
   CKC(cudaMalloc(&e->r_nactive, 4));
   CKC(cudaMallocHost(&e->h_nactive, 8));  // [active points, fallback count of the streaming K1]
+  CKC(cudaMalloc(&e->d_status, 2 * sizeof(int)));
+  CKC(cudaMemsetAsync(e->d_status, 0, 2 * sizeof(int), e->stream));
+  CKC(cudaMallocHost(&e->h_status, 2 * sizeof(int)));
   CKC(cudaMalloc(&e->dbg_sigma, 64 * 8));
   CKC(cudaMalloc(&e->dbg_info, 16 * 4));
   CKC(cudaEventCreate(&e->ev0));
@@ -1063,7 +1113,7 @@ int tnsu_set_tensor(tnsu_engine *e, int t, const void *host, int64_t elems) {
   if (elems != tnsu_tensor_elems(e, t))
     return fail(e, TNSU_E_ARG, "set_tensor: tensor %d has %lld elements per point, got %lld", t,
                 (long long)tnsu_tensor_elems(e, t), (long long)elems);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   CK(cudaMemcpy2DAsync(e->tens[t], e->cap[t] * e->ssz, host, elems * e->ssz, elems * e->ssz, e->batch,
                        cudaMemcpyHostToDevice, e->stream));
   reset_scale_kernel<<<(e->batch + 255) / 256, 256, 0, e->stream>>>(e->tscale, e->n, e->batch, t);
@@ -1078,8 +1128,8 @@ int tnsu_get_tensor(tnsu_engine *e, int t, void *host, int64_t elems) {
   if (elems != tnsu_tensor_elems(e, t))
     return fail(e, TNSU_E_ARG, "get_tensor: tensor %d has %lld elements per point, got %lld", t,
                 (long long)tnsu_tensor_elems(e, t), (long long)elems);
-  CK(cudaSetDevice(e->device));
-  dim3 grid((unsigned)std::min<long long>((elems + 255) / 256, 1024), e->batch);
+  ON_DEVICE(e);
+  dim3 grid((unsigned)std::min<long long>((elems + 255) / 256, 1024), (unsigned)std::min(e->batch, 32768));
   if (e->dtype == TNSU_C128)
     apply_scale_kernel<cplx><<<grid, 256, 0, e->stream>>>((cplx *)e->tens[t], e->cap[t], elems, e->batch, e->tscale, e->n, t);
   else
@@ -1089,15 +1139,14 @@ int tnsu_get_tensor(tnsu_engine *e, int t, void *host, int64_t elems) {
   CK(cudaGetLastError());
   CK(cudaMemcpy2DAsync(host, elems * e->ssz, e->tens[t], e->cap[t] * e->ssz, elems * e->ssz, e->batch,
                        cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return TNSU_OK;
+  return poll_status(e);
 }
 
 int tnsu_set_weights(tnsu_engine *e, int edge, const double *host, int len) {
   if (!e) return TNSU_E_ARG;
   if (!host || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "set_weights: bad argument");
   if (len != e->dims[edge]) return fail(e, TNSU_E_ARG, "set_weights: edge %d has dimension %d, got %d", edge, e->dims[edge], len);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   CK(cudaMemcpy2DAsync(e->weights + (size_t)edge * e->dcap, (size_t)e->m * e->dcap * 8, host, (size_t)len * 8,
                        (size_t)len * 8, e->batch, cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1108,15 +1157,14 @@ int tnsu_get_weights(tnsu_engine *e, int edge, double *host, int len) {
   if (!e) return TNSU_E_ARG;
   if (!host || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "get_weights: bad argument");
   if (len != e->dims[edge]) return fail(e, TNSU_E_ARG, "get_weights: edge %d has dimension %d, got %d", edge, e->dims[edge], len);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   CK(cudaMemcpy2DAsync(host, (size_t)len * 8, e->weights + (size_t)edge * e->dcap, (size_t)e->m * e->dcap * 8,
                        (size_t)len * 8, e->batch, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return TNSU_OK;
+  return poll_status(e);
 }
 
 static int upload_c128(tnsu_engine *e, void *dst, const void *src_c128, size_t count) {
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   if (e->dtype == TNSU_C128) {
     CK(cudaMemcpyAsync(dst, src_c128, count * 16, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1133,7 +1181,7 @@ static int upload_c128(tnsu_engine *e, void *dst, const void *src_c128, size_t c
 int tnsu_reserve_gate_slots(tnsu_engine *e, int n_slots) {
   if (!e) return TNSU_E_ARG;
   if (n_slots < 1) return fail(e, TNSU_E_ARG, "n_slots must be >= 1");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   CK(cudaStreamSynchronize(e->stream));
   if (e->gates) CK(cudaFree(e->gates));
   e->gates = nullptr;
@@ -1165,7 +1213,7 @@ int tnsu_set_hamiltonians(tnsu_engine *e, const void *ham) {
 int tnsu_sweep(tnsu_engine *e, int slot, int n_sweeps) {
   if (!e) return TNSU_E_ARG;
   if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "sweep: gates of slot %d not set", slot);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   e->last_n = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   for (int s = 0; s < n_sweeps; ++s) {
@@ -1181,7 +1229,7 @@ int tnsu_profile_sweep(tnsu_engine *e, int slot, double *ms_out) {
   if (!e) return TNSU_E_ARG;
   if (!ms_out) return fail(e, TNSU_E_ARG, "profile_sweep: null");
   if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "profile_sweep: gates of slot %d not set", slot);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   e->profile = true;
   e->prof_ms[0] = e->prof_ms[1] = e->prof_ms[2] = 0.0;
   int rc = one_sweep(e, slot, nullptr, nullptr);
@@ -1193,6 +1241,7 @@ int tnsu_profile_sweep(tnsu_engine *e, int slot, double *ms_out) {
 
 int tnsu_last_sweep_kernel_ms(tnsu_engine *e, double *total_ms, int32_t *n_launches) {
   if (!e) return TNSU_E_ARG;
+  ON_DEVICE(e);
   if (!e->timed) return fail(e, TNSU_E_STATE, "no sweep has been timed");
   CK(cudaEventSynchronize(e->ev1));
   float ms = 0.f;
@@ -1205,10 +1254,13 @@ int tnsu_last_sweep_kernel_ms(tnsu_engine *e, double *total_ms, int32_t *n_launc
 int tnsu_sweep_error(tnsu_engine *e, double *err_out) {
   if (!e) return TNSU_E_ARG;
   if (!err_out) return fail(e, TNSU_E_ARG, "sweep_error: null");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   std::vector<double> h((size_t)e->batch * e->m);
   CK(cudaMemcpyAsync(h.data(), e->edge_err, h.size() * 8, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  {
+    int rc = poll_status(e);
+    if (rc) return rc;
+  }
   for (int b = 0; b < e->batch; ++b) {
     double mx = 0.0;
     bool bad = false;
@@ -1242,7 +1294,7 @@ int tnsu_energy(tnsu_engine *e, double *energy_out) {
   if (!e) return TNSU_E_ARG;
   if (!energy_out) return fail(e, TNSU_E_ARG, "energy: null");
   if (!e->hams_set) return fail(e, TNSU_E_STATE, "energy: Hamiltonians not set");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   int rc = ensure_static_descs(e);
   if (rc) return rc;
   rc = energy_launch(e, nullptr, nullptr);
@@ -1255,7 +1307,7 @@ int tnsu_energy(tnsu_engine *e, double *energy_out) {
 int tnsu_pair_rdm(tnsu_engine *e, int edge, void *rdm) {
   if (!e) return TNSU_E_ARG;
   if (!rdm || edge < 0 || edge >= e->m) return fail(e, TNSU_E_ARG, "pair_rdm: bad argument");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   int rc = ensure_static_descs(e);
   if (rc) return rc;
   if (e->dtype == TNSU_C128)
@@ -1269,7 +1321,7 @@ int tnsu_pair_rdm(tnsu_engine *e, int edge, void *rdm) {
 }
 
 static int site_rdms(tnsu_engine *e, std::vector<cplx> &h) {
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   int rc = upload_site_descs(e);
   if (rc) return rc;
   if (e->dcap > 64) return fail(e, TNSU_E_UNSUPPORTED, "site RDM: bond dimension above 64");
@@ -1324,7 +1376,7 @@ int tnsu_expectation_per_site(tnsu_engine *e, const void *op, void *out) {
 int tnsu_pair_expectation_per_site(tnsu_engine *e, const void *op, void *out) {
   if (!e) return TNSU_E_ARG;
   if (!op || !out) return fail(e, TNSU_E_ARG, "pair_expectation_per_site: null");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   int rc = ensure_static_descs(e);
   if (rc) return rc;
   rc = upload_c128(e, e->op_buf, op, (size_t)e->d4);
@@ -1345,7 +1397,7 @@ int tnsu_pair_expectation_per_site(tnsu_engine *e, const void *op, void *out) {
 
 int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_iterations, double tol, int log_cap,
              int32_t *n_checks, double *log_error, double *log_energy, int32_t *log_slot, int32_t *log_step,
-             int32_t *converged, int32_t *total_sweeps) {
+             int32_t *converged, int32_t *total_sweeps, int32_t *final_slot) {
   if (!e) return TNSU_E_ARG;
   if (n_dts < 0 || n_dts > e->n_slots) return fail(e, TNSU_E_ARG, "run: %d time steps but %d gate slots", n_dts, e->n_slots);
   for (int s = 0; s < n_dts; ++s)
@@ -1353,7 +1405,7 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
   if (!e->hams_set) return fail(e, TNSU_E_STATE, "run: Hamiltonians not set");
   if (!is_last_value && n_dts > 0) return fail(e, TNSU_E_ARG, "run: null is_last_value");
   if (log_cap < 0) return fail(e, TNSU_E_ARG, "run: negative log_cap");
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   const size_t B = e->batch;
   // (re)allocate logs
   if (log_cap > e->r_log_cap || !e->r_log_err) {
@@ -1485,8 +1537,11 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
           break;
         }
         if (2LL * e->h_nactive[1] > e->lqc_attempted) e->lqc_suspend_until = it + 1 + 32;
+        e->lqc_flagged_total += e->h_nactive[1];
         e->lqc_attempted = 0;
       }
+      rc_loop = poll_status(e);
+      if (rc_loop != TNSU_OK) break;
     }
   }
   e->run_sweep_index = 0;
@@ -1499,6 +1554,7 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
   if (n_checks) CK(cudaMemcpy(n_checks, e->r_nchecks, B * 4, cudaMemcpyDeviceToHost));
   if (converged) CK(cudaMemcpy(converged, e->r_conv, B * 4, cudaMemcpyDeviceToHost));
   if (total_sweeps) CK(cudaMemcpy(total_sweeps, e->r_step, B * 4, cudaMemcpyDeviceToHost));
+  if (final_slot) CK(cudaMemcpy(final_slot, e->r_slot, B * 4, cudaMemcpyDeviceToHost));
   if (log_cap > 0) {
     size_t w = (size_t)log_cap, pitch = (size_t)e->r_log_cap;
     if (log_error) CK(cudaMemcpy2D(log_error, w * 8, e->r_log_err, pitch * 8, w * 8, B, cudaMemcpyDeviceToHost));
@@ -1513,8 +1569,32 @@ void *tnsu_stream(tnsu_engine *e) { return e ? (void *)e->stream : nullptr; }
 
 int tnsu_synchronize(tnsu_engine *e) {
   if (!e) return TNSU_E_ARG;
-  CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
+  ON_DEVICE(e);
+  return poll_status(e);
+}
+
+int tnsu_stats(tnsu_engine *e, int64_t *out, int n_out) {
+  if (!e) return TNSU_E_ARG;
+  if (!out || n_out < 0) return fail(e, TNSU_E_ARG, "stats: bad argument");
+  ON_DEVICE(e);
+  if (e->lq_stats != nullptr) {
+    int flagged = 0;
+    CK(cudaMemcpyAsync(&flagged, e->lq_stats, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemsetAsync(e->lq_stats, 0, sizeof(int), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->lqc_flagged_total += flagged;
+  }
+  {
+    CK(cudaMemcpyAsync(e->h_status, e->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->h_status[1]) {  // the non-finite flag stays for the next polling entry point
+      e->svd_unconverged_total += e->h_status[1];
+      CK(cudaMemsetAsync(e->d_status + 1, 0, sizeof(int), e->stream));
+    }
+  }
+  const int64_t v[TNSU_N_STATS] = {e->launches, e->lqc_attempted_total, e->lqc_flagged_total, e->svd_unconverged_total,
+                                   e->nonfinite_events, e->fused_runs};
+  for (int i = 0; i < n_out && i < TNSU_N_STATS; ++i) out[i] = v[i];
   return TNSU_OK;
 }
 
@@ -1524,7 +1604,7 @@ int tnsu_debug_edge(tnsu_engine *e, int slot, int edge, int point, void *l_i, vo
   if (!e) return TNSU_E_ARG;
   if (edge < 0 || edge >= e->m || point < 0 || point >= e->batch) return fail(e, TNSU_E_ARG, "debug_edge: bad argument");
   if (slot < 0 || slot >= e->n_slots || !e->slot_set[slot]) return fail(e, TNSU_E_STATE, "debug_edge: gates of slot %d not set", slot);
-  CK(cudaSetDevice(e->device));
+  ON_DEVICE(e);
   // A single edge out of sweep order: plan from the current dims, then only that edge's descriptor is
   // valid if no earlier edge of the plan changes a dimension it sees (true in steady state).
   if (!e->plan_valid) {

@@ -844,20 +844,10 @@ static inline int rcc_smem_bytes(int ldm) { return LQC_CHUNK * 4 + TNSU_MAX_LEGS
 template <int MB>
 cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flags, cudaStream_t st) {
   auto kern = lq_chol_kernel<MB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   if (p.lqc_force_fallback != 2) {  // default: one warp per (item, side); 2 selects the two-warp-CTA kernel (A/B comparisons)
     auto kw = lq_chol_warp_kernel<MB>;
-    static bool attr_w = false;
-    if (!attr_w) {
-      cudaError_t s = cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-      if (s != cudaSuccess) return s;
-      attr_w = true;
-    }
+    if (cudaError_t s = tnsu_opt_in_smem((const void *)kw); s != cudaSuccess) return s;
     const int per_warp = lqw_smem_bytes_per_warp(MB);
     kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
     return cudaGetLastError();
@@ -868,12 +858,7 @@ cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flag
 template <int MB>
 cudaError_t launch_rc_chol_v(const EdgeLaunch<double> &p, int n_items, const int *flags, cudaStream_t st) {
   auto kern = recompose_chol_kernel<MB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<2 * n_items, RCC_THREADS, rcc_smem_bytes(p.ldm), st>>>(p, flags);
   return cudaGetLastError();
 }

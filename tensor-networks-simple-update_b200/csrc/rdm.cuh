@@ -675,11 +675,12 @@ __global__ void __launch_bounds__(RDM_THREADS) site_rdm_kernel(const SiteDesc *d
 template <typename S>
 __global__ void apply_scale_kernel(S *base, long long point_stride, long long elems, int batch, const double *tscale,
                                    int n_tensors, int t) {
-  const int b = blockIdx.y;
-  const double sc = tscale[(size_t)b * n_tensors + t];
-  S *ptr = base + (size_t)b * point_stride;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x)
-    ptr[i] = ptr[i] * sc;
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {  // gridDim.y is capped at 65535: stride over the points
+    const double sc = tscale[(size_t)b * n_tensors + t];
+    S *ptr = base + (size_t)b * point_stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x)
+      ptr[i] = ptr[i] * sc;
+  }
 }
 __global__ void reset_scale_kernel(double *tscale, int n_tensors, int batch, int t) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

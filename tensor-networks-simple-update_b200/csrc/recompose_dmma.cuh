@@ -227,12 +227,7 @@ template <int MBO, int KB>
 cudaError_t launch_recompose_dmma_v(const EdgeLaunch<double> &p, int n_items, int ncl_cap, cudaStream_t st) {
   auto kern = recompose_dmma_kernel<MBO, KB>;
   const int smem = rcd_smem_bytes(ncl_cap, p.ldm);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<2 * n_items * p.cluster, RCD_THREADS, smem, st>>>(p, ncl_cap);
   return cudaGetLastError();
 }

@@ -451,8 +451,10 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
 
   const long long clk_b = clock64();
   int sweeps = 0;
+  bool jacobi_done = false;
+  const int max_sweeps = min(p.svd_max_sweeps, SVDW_MAX_SWEEPS);
   if constexpr (ACCV) {
-    for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
+    for (; sweeps < max_sweeps; ++sweeps) {
       bool rotated = false;
       for (int st = 0; st < NP; ++st) {
         // step A: pairs (x_k, y_k)
@@ -474,13 +476,14 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
       }
       if (!__any_sync(0xffffffffu, rotated)) {
         ++sweeps;
+        jacobi_done = true;
         break;
       }
     }
   } else {
     // one half step per trip (step A: pair (x_k, y_k), then x_k <- x_{k+1}; step B: pair (y_k, x_k), the last
     // processor idle, then x_k <- x_{k-1}): a single copy of the step in the instruction stream
-    for (; sweeps < SVDW_MAX_SWEEPS; ++sweeps) {
+    for (; sweeps < max_sweeps; ++sweeps) {
       bool rotated = false;
 #pragma unroll 1
       for (int st = 0; st < 2 * NP; ++st) {
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
       }
       if (!__any_sync(0xffffffffu, rotated)) {
         ++sweeps;
+        jacobi_done = true;
         break;
       }
     }
@@ -542,6 +546,8 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
     const double mine = (sel_x ? sx : 0.0) + (sel_y ? sy : 0.0);
     for (int j = 0; j < NP; ++j) tot += __shfl_sync(0xffffffffu, mine, in_group ? base + 2 * j : lane);
   }
+  if (valid && gl == 0 && !(tot > 0.0 && tot < 1e300)) atomicOr(p.status, 1);  // NaN / Inf in the state (or theta == 0)
+  if (!jacobi_done && lane == 0) atomicAdd(p.status + 1, 1);
   // lambda' = s / sum(s)  (reference :296) and this edge's convergence error (:196-206)
   double e2 = 0.0;
   if (sel_x) {
@@ -769,12 +775,7 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
 template <int R, bool ACCV>
 cudaError_t launch_svd_warp_r(const EdgeLaunch<double> &p, int n_items, cudaStream_t st) {
   auto kern = svd_warp_kernel<R, ACCV>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t s = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TNSU_SMEM_LIMIT);
-    if (s != cudaSuccess) return s;
-    attr_done = true;
-  }
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   const int gpw = 32 / (2 * p.svdw_np);
   const int per_cta = (SVDW_THREADS / 32) * gpw;
   const int smem = per_cta * p.svdw_group_doubles * 8;

@@ -15,6 +15,6 @@ from .math_objects import spin_operators  # noqa: F401
 from .tensor_network import TensorNetwork  # noqa: F401
 from .simple_update import SimpleUpdate, SimpleUpdateBatch, per_point  # noqa: F401
 from .engine import Engine  # noqa: F401
-from ._lib import EngineError  # noqa: F401
+from ._lib import EngineError, NonFiniteError  # noqa: F401
 
 __version__ = "0.1.0"

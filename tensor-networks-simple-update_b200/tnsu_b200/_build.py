@@ -24,8 +24,9 @@ def _sources_digest() -> str:
         if name.endswith((".cu", ".cuh")):
             with open(os.path.join(CSRC, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
-    with open(os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include", "tnsu_b200.h"), "rb") as f:
-        h.update(f.read())
+    for header in ("tnsu_b200.h", "tnsu_b200_debug.h"):
+        with open(os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include", header), "rb") as f:
+            h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtnsu_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TNSU_F64, TNSU_C128 = 0, 1
 ERRORS = {-1: "TNSU_E_ARG", -2: "TNSU_E_UNSUPPORTED", -3: "TNSU_E_CUDA", -4: "TNSU_E_NONFINITE", -5: "TNSU_E_STATE"}
@@ -17,7 +17,8 @@ _i64p = C.POINTER(C.c_int64)
 _f64p = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
-# name -> (restype, argtypes); every symbol declared in include/tnsu_b200.h
+# name -> (restype, argtypes); every symbol declared in include/tnsu_b200.h (the drop-in boundary) and
+# include/tnsu_b200_debug.h (profiling / debugging)
 PROTOTYPES = {
     "tnsu_abi_version": (C.c_int, []),
     "tnsu_last_error": (C.c_char_p, [_vp]),
@@ -44,11 +45,12 @@ PROTOTYPES = {
     "tnsu_pair_expectation_per_site": (C.c_int, [_vp, _vp, _vp]),
     "tnsu_expectation_per_site": (C.c_int, [_vp, _vp, _vp]),
     "tnsu_run": (C.c_int, [_vp, C.c_int, _i32p, C.c_int, C.c_double, C.c_int, _i32p, _f64p, _f64p, _i32p, _i32p,
-                           _i32p, _i32p]),
+                           _i32p, _i32p, _i32p]),
     "tnsu_stream": (_vp, [_vp]),
     "tnsu_synchronize": (C.c_int, [_vp]),
     "tnsu_launch_count": (C.c_int64, [_vp]),
     "tnsu_last_sweep_kernel_ms": (C.c_int, [_vp, _f64p, _i32p]),
+    "tnsu_stats": (C.c_int, [_vp, _i64p, C.c_int]),
     "tnsu_profile_sweep": (C.c_int, [_vp, C.c_int, _f64p]),
     "tnsu_debug_edge": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _f64p, _i32p]),
 }
@@ -62,6 +64,15 @@ class EngineError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"{ERRORS.get(code, code)}: {message}")
         self.code = code
+
+
+class NonFiniteError(EngineError, ValueError):
+    """TNSU_E_NONFINITE: NaN / Inf met during an update.  Also a ValueError, which is what the reference raises
+    there (scipy.linalg.rq / svd run with check_finite=True, simple_update.py:243-250, :404)."""
+
+
+def error_from_code(code: int, message: str) -> EngineError:
+    return NonFiniteError(code, message) if code == -4 else EngineError(code, message)
 
 
 def load():

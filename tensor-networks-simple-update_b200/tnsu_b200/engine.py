@@ -45,7 +45,7 @@ class Engine:
     # -- plumbing --
     def _check(self, rc):
         if rc != 0:
-            raise _lib.EngineError(rc, self._lib.tnsu_last_error(self._h).decode())
+            raise _lib.error_from_code(rc, self._lib.tnsu_last_error(self._h).decode())
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -164,13 +164,13 @@ class Engine:
         f64 = lambda *s: np.zeros(s, dtype=np.float64)  # noqa: E731
         res = dict(n_checks=i32(self.batch), log_error=f64(self.batch, cap), log_energy=f64(self.batch, cap),
                    log_slot=i32(self.batch, cap), log_step=i32(self.batch, cap), converged=i32(self.batch),
-                   sweeps=i32(self.batch))
+                   sweeps=i32(self.batch), final_slot=i32(self.batch))
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
         fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         self._check(self._lib.tnsu_run(self._h, n_dts, ip(last), int(max_iterations), float(tol), cap,
                                        ip(res["n_checks"]), fp(res["log_error"]), fp(res["log_energy"]),
                                        ip(res["log_slot"]), ip(res["log_step"]), ip(res["converged"]),
-                                       ip(res["sweeps"])))
+                                       ip(res["sweeps"]), ip(res["final_slot"])))
         return res
 
     # -- instrumentation --
@@ -184,6 +184,15 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.tnsu_launch_count(self._h))
+
+    STAT_NAMES = ("launches", "lq_streamed", "lq_flagged", "svd_unconverged", "nonfinite_events", "fused_runs")
+
+    def stats(self) -> dict:
+        """Cumulative counters of this handle (tnsu_stats): what the streaming reduction was given and what came back
+        flagged for the Householder fallback, Jacobi iterations that hit their sweep limit, non-finite events."""
+        out = np.zeros(len(self.STAT_NAMES), dtype=np.int64)
+        self._check(self._lib.tnsu_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), len(out)))
+        return dict(zip(self.STAT_NAMES, (int(x) for x in out)))
 
     def last_sweep_kernel_ms(self):
         ms = C.c_double()

@@ -20,6 +20,19 @@ from .engine import Engine
 from .tensor_network import TensorNetwork
 
 _NO_TRUNCATION = 1 << 20  # d_max=None in the reference means "keep everything"
+_FINGERPRINT_SAMPLES = 1 << 16
+
+
+def _fingerprint(a):
+    """Cheap content stamp of an array: shape, dtype and the sum over (at most 65 536 evenly strided) elements.  The
+    reference reads tensors / weights at call time, so an in-place edit (`tn.tensors[0] *= 2`,
+    `tn.weights[3][:] = ...`) between two calls must reach the device: the wrapper re-uploads when a stamp changed.
+    Arrays larger than the sample are strided — a single-element edit of a huge array can go unseen; replace the list
+    entry or call `upload_state()` then."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // _FINGERPRINT_SAMPLES)
+    return a.shape, a.dtype.str, complex(np.add.reduce(flat[::step]))
 
 
 def _per_point(value, n_points, name):
@@ -49,8 +62,11 @@ class SimpleUpdateBatch:
     All points use dt schedules of the same LENGTH (values may differ)."""
 
     def __init__(self, tensor_networks, j_ij, h_k, s_i, s_j, s_k, dts, d_max=2, max_iterations=1000,
-                 convergence_error=1e-6, hamiltonian=None, device=0, stream=None):
+                 convergence_error=1e-6, hamiltonian=None, device=0, stream=None, detect_inplace_edits=False):
         self.tensor_networks = list(tensor_networks)
+        # content stamps per array on every call: on for the one-network drop-in facade, off by default for large
+        # batches (one numpy reduction per array and call; list-entry replacement is always detected)
+        self.detect_inplace_edits = detect_inplace_edits
         self.n_points = len(self.tensor_networks)
         if self.n_points == 0:
             raise ValueError("at least one tensor network is required")
@@ -77,6 +93,7 @@ class SimpleUpdateBatch:
         self._hams_uploaded_obj = None
         self._synced = None
         self._synced_engine = None
+        self._state_complex = None
         self.results = None
 
     # ------------------------------------------------------------------ host-side operators
@@ -175,11 +192,14 @@ class SimpleUpdateBatch:
         tn = self.tensor_networks[0]
         return [len(w) for w in tn.weights]
 
-    def _wants_complex(self, extra=()):
-        for tn in self.tensor_networks:
-            for t in tn.tensors:
-                if np.iscomplexobj(t) and np.any(np.imag(t) != 0.0):
-                    return True
+    def _wants_complex(self, extra=(), in_sync=False):
+        """complex128 engine needed?  The tensors are scanned only when they are about to be (re-)uploaded; while the
+        device state is the current one the answer of that scan is reused."""
+        if not in_sync or self._state_complex is None:
+            self._state_complex = any(np.iscomplexobj(t) and np.any(np.imag(t) != 0.0)
+                                      for tn in self.tensor_networks for t in tn.tensors)
+        if self._state_complex:
+            return True
         for a in extra:
             if np.iscomplexobj(a) and np.any(np.imag(a) != 0.0):
                 return True
@@ -189,7 +209,8 @@ class SimpleUpdateBatch:
         """Create (or re-create when shapes / dtype changed) the engine and upload the host state."""
         dims = self._current_dims()
         hams = self._all_hamiltonians()
-        need_complex = self._wants_complex((hams,) + tuple(extra_ops)) or any(
+        in_sync = self._state_in_sync()
+        need_complex = self._wants_complex((hams,) + tuple(extra_ops), in_sync) or any(
             np.iscomplexobj(np.asarray(x)) and np.any(np.imag(np.asarray(x)) != 0.0) for dts in self.dts for x in dts)
         d_max = _NO_TRUNCATION if self.d_max is None else int(self.d_max)
         eng = self._engine
@@ -206,26 +227,31 @@ class SimpleUpdateBatch:
         if not self._hams_uploaded or self._hams_uploaded_obj is not hams:
             eng.set_hamiltonians(hams)
             self._hams_uploaded, self._hams_uploaded_obj = True, hams
-        if not self._state_in_sync():
+        if not (in_sync and self._synced_engine is eng):
             self.upload_state()
         return eng
 
     def _state_in_sync(self):
-        """True when every tensor / weight array object is the one last uploaded to or downloaded from the device.
-        The reference replaces list entries when it updates (:294-296); in-place edits of an array are NOT seen —
-        replace the entry or call upload_state()."""
+        """True when every tensor / weight array is the object last uploaded to or downloaded from the device AND its
+        content stamp is unchanged: the reference replaces list entries when it updates (:294-296) and reads the
+        arrays at call time, so both a replaced entry and an in-place edit must trigger a re-upload."""
         refs = getattr(self, "_synced", None)
         if refs is None or self._synced_engine is not self._engine:
             return False
-        for tn, (ts, ws) in zip(self.tensor_networks, refs):
+        for tn, (ts, ws, stamps) in zip(self.tensor_networks, refs):
             if len(tn.tensors) != len(ts) or len(tn.weights) != len(ws):
                 return False
             if any(a is not b for a, b in zip(tn.tensors, ts)) or any(a is not b for a, b in zip(tn.weights, ws)):
                 return False
+            if stamps is not None and stamps != [_fingerprint(a) for a in list(tn.tensors) + list(tn.weights)]:
+                return False
         return True
 
     def _mark_synced(self):
-        self._synced = [(list(tn.tensors), list(tn.weights)) for tn in self.tensor_networks]
+        stamp = self.detect_inplace_edits
+        self._synced = [(list(tn.tensors), list(tn.weights),
+                         [_fingerprint(a) for a in list(tn.tensors) + list(tn.weights)] if stamp else None)
+                        for tn in self.tensor_networks]
         self._synced_engine = self._engine
 
     def upload_state(self):
@@ -292,6 +318,7 @@ class SimpleUpdateBatch:
                 "energy": [float(x) for x in res["log_energy"][p, :k]],
                 "converged": bool(res["converged"][p]),
                 "sweeps": int(res["sweeps"][p]),
+                "final_dt": self.dts[p][int(res["final_slot"][p])],
             })
         self.results = loggers
         return loggers
@@ -361,7 +388,7 @@ class SimpleUpdate:
         if b is None or b.tensor_networks[0] is not self.tensor_network:
             b = SimpleUpdateBatch([self.tensor_network], self.j_ij, self.h_k, self.s_i, self.s_j, self.s_k,
                                   list(self.dts), self.d_max, self.max_iterations, self.convergence_error,
-                                  self.hamiltonian, device=self.device)
+                                  self.hamiltonian, device=self.device, detect_inplace_edits=True)
             self._batch = b
         b.j_ij, b.h_k, b.hamiltonian = [self.j_ij], [self.h_k], [self.hamiltonian]
         b.s_i, b.s_j, b.s_k = self.s_i, self.s_j, self.s_k
@@ -375,31 +402,78 @@ class SimpleUpdate:
 
     # ---- run loop (:107-194) ----
     def run(self):
+        """The whole dt / iteration / convergence loop.  With print_process=False it runs on the device in one call
+        (tnsu_run: per-point state machine, no host round trip per sweep); with print_process=True the same loop is
+        driven from here check by check so that every progress line appears live with its wall-clock times, exactly
+        as the reference prints them (:142-172)."""
         error = np.inf
         impl = self._impl()
         if len(self.dts) > 0 and self.max_iterations > 0:
-            log = impl.run()[0]
-            for err, dt, it, en in zip(log["error"], log["dt"], log["iteration"], log["energy"]):
-                self.logger["error"].append(err)
-                self.logger["dt"].append(dt)
-                self.logger["iteration"].append(it)
+            if self.print_process:
+                error = self._run_verbose(impl)
+                if self.converged:
+                    return
+            else:
+                log = impl.run()[0]
+                self.logger["error"] += log["error"]
+                self.logger["dt"] += log["dt"]
+                self.logger["iteration"] += log["iteration"]
                 if self.log_energy:
-                    self.logger["energy"].append(en)
-                if self.print_process:
-                    print("| D max: {:2d} | dt: {:8.6f} | iteration: {:5d}/{:5d} | convergence error: {:13.10f} | "
-                          "energy per-site: {: 16.11f} | iteration time: {:5.1f} sec | tot time:{:7.1f} min".format(
-                              self.d_max, np.real(dt), it, self.max_iterations, err, np.round(en, 10), 0.0, 0.0))
-            if log["error"]:
-                error = log["error"][-1]
-            if log["dt"]:
-                self.dt = log["dt"][-1]
-            self.converged = log["converged"]
+                    self.logger["energy"] += log["energy"]
+                if log["error"]:
+                    error = log["error"][-1]
+                self.dt = log["final_dt"]
+                self.converged = log["converged"]
+        elif len(self.dts) > 0:
+            self.dt = self.dts[-1]
         self.tensor_network.su_logger = self.logger
         if self.converged:
             print("==> Simple Update converged. final error is {:4.10f} < {:4.10f}.".format(error, self.convergence_error))
         else:
             print("==> Simple Update did not converged. final error is {:4.10f} > {:4.10f}.".format(
                 error, self.convergence_error))
+
+    def _run_verbose(self, impl: "SimpleUpdateBatch"):
+        """run() driven from the host (reference :117-188 line by line): sweeps, convergence error and energy are the
+        same device kernels, called through tnsu_sweep / tnsu_sweep_error / tnsu_energy."""
+        import time
+
+        eng = impl._ensure_engine()
+        impl._set_schedule_gates()
+        error, total_time, step = np.inf, 0.0, 0
+        try:
+            for slot, dt in enumerate(self.dts):
+                start_time = time.time()
+                self.dt = dt
+                for i in range(self.max_iterations):
+                    step += 1
+                    eng.sweep(slot, 1)
+                    if i % 2 == 0 and i > 0:
+                        error = float(eng.sweep_error()[0])
+                        elapsed = time.time() - start_time
+                        total_time += elapsed
+                        energy = float(eng.energy()[0])
+                        self.logger["error"].append(error)
+                        self.logger["dt"].append(dt)
+                        self.logger["iteration"].append(step)
+                        if self.log_energy:
+                            self.logger["energy"].append(energy)
+                        print("| D max: {:2d} | dt: {:8.6f} | iteration: {:5d}/{:5d} | convergence error: {:13.10f} | "
+                              "energy per-site: {: 16.11f} | iteration time: {:5.1f} sec | tot time:{:7.1f} min".format(
+                                  self.d_max, dt, i, self.max_iterations, error, np.round(energy, 10), elapsed,
+                                  total_time // 60 + (total_time % 60) / 60))
+                        start_time = time.time()
+                        if error <= self.convergence_error and dt == self.dts[-1]:
+                            self.converged = True
+                            self.tensor_network.su_logger = self.logger
+                            print("==> Simple Update converged. final error is {:4.10f} < {:4.10f}.".format(
+                                error, self.convergence_error))
+                            return error
+                        if error <= self.convergence_error:
+                            break
+        finally:
+            impl.download_state()
+        return error
 
     def compute_convergence_error(self):
         """max_e ||lambda_e(old) - lambda_e(new)||_2 (:196-206).  With explicit old_weights the host lists are

@@ -93,7 +93,7 @@ def test_tensor_network_container(tnsu, tmp_path, capsys):
 def test_library_exports_every_declared_symbol():
     from tnsu_b200 import _lib
 
-    header = open(os.path.join(ROOT, "include", "tnsu_b200.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("tnsu_b200.h", "tnsu_b200_debug.h"))
     declared = set(re.findall(r"\b(tnsu_[a-z0-9_]+)\s*\(", header))
     declared.discard("tnsu_engine")
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)

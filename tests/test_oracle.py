@@ -14,7 +14,8 @@ import tnsu_oracle as orc
 from conftest import GOLDEN, build_case, load_golden, unpack_list
 
 LIGHT_SWEEPS = ["star_D2", "tfi_D4", "chain_growth", "peps_growth", "pyro_field", "star_complex", "cube_D2",
-                "obc4x3_D3", "kagome_spin1", "pbc3_D2_dt0", "peps_D8"]
+                "obc4x3_D3", "kagome_spin1", "pbc3_D2_dt0", "peps_D8", "peps_D8_complex", "tfi_D4_complex_dt",
+                "star_D3_imag_dt"]
 
 
 def test_recorded_deviations_are_at_rounding_level():
@@ -22,6 +23,12 @@ def test_recorded_deviations_are_at_rounding_level():
     assert manifest["cases"]["pkl_afh_10x10_obc_D4"]["vs_known"] < 1e-13  # reference tests/test_main.py:35
     for name, c in cases.CASES.items():
         g = load_golden(("sweep_" if c["kind"] == "sweep" else "run_") + name)
+        if c.get("ref_sensitive"):
+            # rounding-amplifying trajectories (see oracle/cases.py): the reference and its restatement agree to
+            # 1e-8 only; the control flow (number of checks) is still identical
+            assert float(g["oracle_dev_energy"]) < 1e-9 and float(g["oracle_dev_weights"]) < 1e-7, name
+            assert int(g["oracle_dev_checks"]) == 0, name
+            continue
         assert float(g["oracle_dev_energy"]) < 1e-12, name
         assert float(g["oracle_dev_weights"]) < 1e-12, name
         if c["kind"] == "sweep":
@@ -56,6 +63,11 @@ def test_oracle_sweeps_match_reference(name):
     for t in sorted({0, smat.shape[0] - 1}):
         assert np.abs(orc.site_rdm(tensors, weights, smat, t) - g[f"site_rdm_{t}"]).max() < 1e-12
     assert abs(orc.expectation_per_site(tensors, weights, smat, case["s_i"][-1]) - float(g["expect1"])) < 1e-12
+    d = case["d"]
+    op2 = np.reshape(np.kron(case["s_i"][-1], case["s_j"][0]), (d, d, d, d))
+    assert abs(orc.pair_expectation_per_site(tensors, weights, smat, op2) - float(np.real(g["pair_expect_per_site"]))) < 1e-12
+    for e, ref in zip(sorted({0, m // 2, m - 1}), g["pair_expect_edge"]):
+        assert abs(orc.pair_expectation(tensors, weights, smat, e, op2) - ref) < 1e-12
 
 
 def test_oracle_known_answer_pickled_state(tnsu):
@@ -69,10 +81,11 @@ def test_oracle_known_answer_pickled_state(tnsu):
     assert abs(orc.energy_per_site(tensors, weights, smat, model) - -0.5616206254235453) < 1e-13
 
 
-def test_oracle_full_run_matches_reference():
-    """README star config (BASELINE config 1): whole run(), seed 42."""
-    case = build_case("run_star_D2")
-    g = load_golden("run_run_star_D2")
+@pytest.mark.parametrize("name", ["run_star_D2", "run_star_D3_complex"])
+def test_oracle_full_run_matches_reference(name):
+    """README star config (BASELINE config 1): whole run(), seed 42; and a complex128 run (complex start, Sy field)."""
+    case = build_case(name)
+    g = load_golden("run_" + name)
     tensors, weights, model = _seeded(case)
     log = orc.run(tensors, weights, case["smat"], model, case["dts"], case["d_max"], case["max_iterations"], case["tol"])
     assert len(log["error"]) == len(g["log_error"]) and log["converged"] == bool(g["converged"])

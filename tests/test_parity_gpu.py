@@ -41,6 +41,7 @@ def test_sweeps_match_reference(tnsu, name):
     tn = make_network(tnsu, case)
     sim = make_su(tnsu, tn, case, [case["dt"]])
     sim.dt = case["dt"]
+    prev_w = [np.array(w) for w in tn.weights]
     for sw in range(case["sweeps"]):
         sim.simple_update()
         ref_w = unpack_list(g, f"weights_s{sw}")
@@ -49,6 +50,15 @@ def test_sweeps_match_reference(tnsu, name):
             assert np.abs(a - b).max() < TOL_W
         e_ref = g["energies"][sw]
         assert abs(sim.energy_per_site() - e_ref) < TOL_E * max(1.0, abs(e_ref))
+        # compute_convergence_error (reference :196-206): the value the kernels accumulated edge by edge, and the
+        # host form with explicit old_weights
+        if all(a.shape == b.shape for a, b in zip(prev_w, ref_w)):
+            err_ref = max(np.sqrt(np.sum(np.square(a - b))) for a, b in zip(prev_w, ref_w))
+            assert abs(sim.compute_convergence_error() - err_ref) < 1e-10
+            sim.old_weights = prev_w
+            assert abs(sim.compute_convergence_error() - err_ref) < 1e-10
+            sim.old_weights = None
+        prev_w = ref_w
     for t in tn.tensors:
         assert t.dtype == np.complex128 and abs(np.linalg.norm(t) - 1.0) < 1e-12  # reference: T / ||T|| (:294-295)
     m = case["smat"].shape[1]
@@ -57,6 +67,13 @@ def test_sweeps_match_reference(tnsu, name):
     for t in sorted({0, case["smat"].shape[0] - 1}):
         assert np.abs(sim.tensor_rdm(t) - g[f"site_rdm_{t}"]).max() < 1e-10
     assert abs(sim.expectation_per_site(case["s_i"][-1]) - float(g["expect1"])) < 1e-10
+    # the two-site observable family and the one-site expectation (reference :595-613, :639-649)
+    d = case["d"]
+    op2 = np.reshape(np.kron(case["s_i"][-1], case["s_j"][0]), (d, d, d, d))
+    assert abs(sim.pair_expectation_per_site(op2) - float(np.real(g["pair_expect_per_site"]))) < 1e-10
+    for e, ref in zip(sorted({0, m // 2, m - 1}), g["pair_expect_edge"]):
+        assert abs(sim.tensor_pair_expectation(e, op2) - ref) < 1e-10
+    assert abs(sim.tensor_expectation(0, case["s_i"][-1]) - g["site_expect_0"]) < 1e-10
     # |T| is gauge invariant only up to the conditioning of the small weights: loose check
     assert np.abs(np.abs(tn.tensors[0]) - g["abs_tensor_0"]).max() < 1e-4
 
@@ -73,16 +90,75 @@ def test_full_run_matches_reference(tnsu, name, capsys):
     assert ("==> Simple Update converged." in out) == bool(g["converged"])
     assert sim.converged == bool(g["converged"])
     assert tn.su_logger is sim.logger
+    # rounding-amplifying trajectories (oracle/cases.py `ref_sensitive`): 20x the spread between the unmodified
+    # reference and its own restatement, which the fixture records; 1e-10 everywhere else
+    tol_w, tol_e = TOL_W, TOL_E
+    if case.get("ref_sensitive"):
+        tol_w, tol_e = 20 * float(g["oracle_dev_weights"]), max(TOL_E, 20 * float(g["oracle_dev_energy"]))
+        assert tol_w < 2e-7 and tol_e < 2e-9
     # identical control flow: same number of convergence checks, at the same sweeps, with the same dt
     assert sim.logger["iteration"] == [int(x) for x in g["log_iteration"]]
     assert np.array_equal(np.array(sim.logger["dt"]), g["log_dt"])
-    assert np.abs(np.array(sim.logger["error"]) - g["log_error"]).max() < 1e-10
-    assert np.abs(np.array(sim.logger["energy"]) - g["log_energy"]).max() < 1e-10
+    assert sim.dt == g["log_dt"][-1]
+    assert np.abs(np.array(sim.logger["error"]) - g["log_error"]).max() < tol_w
+    assert np.abs(np.array(sim.logger["energy"]) - g["log_energy"]).max() < tol_e * max(1.0, np.abs(g["log_energy"]).max())
     e_ref = float(g["energy"])
-    assert abs(sim.energy_per_site() - e_ref) < TOL_E * max(1.0, abs(e_ref))
+    assert abs(sim.energy_per_site() - e_ref) < tol_e * max(1.0, abs(e_ref))
     for a, b in zip(unpack_list(g, "weights"), tn.weights):
-        assert np.abs(a - b).max() < TOL_W
-    assert abs(sim.expectation_per_site(case["s_i"][-1]) - float(g["expect1"])) < 1e-9
+        assert np.abs(a - b).max() < tol_w
+    assert abs(sim.expectation_per_site(case["s_i"][-1]) - float(g["expect1"])) < max(1e-9, 10 * tol_w)
+    st = sim._impl().engine.stats()
+    assert st["svd_unconverged"] == 0 and st["nonfinite_events"] == 0, st
+    if name in ("run_peps_D8", "run_peps_D8_growth", "run_blbq_D4"):
+        # config 2 / 4 shapes go through the streaming CholeskyQR2 reduction, and the small weights of a converged
+        # state (fixture key min_weight) make part of the bond matrices ill-conditioned: the Householder fallback
+        # provably took those
+        assert st["lq_streamed"] > 0 and 0 < st["lq_flagged"] <= st["lq_streamed"], st
+        print(f"{name}: streamed {st['lq_streamed']} flagged {st['lq_flagged']} min weight {float(g['min_weight']):.2e}")
+
+
+def test_known_answer_from_shipped_pickle_via_tnsu_names(capsys):
+    """The reference's own known-answer test (tests/test_main.py:17-35) through the reference's import names: the `tnsu`
+    alias package, `TensorNetwork.load_network` on the shipped pickle (tensor_network.py:207-230), then one Simple-Update
+    sweep warm-started from the loaded state and a save -> load round trip of the result (state I/O)."""
+    import os
+    import tempfile
+
+    import tnsu.simple_update as su
+    import tnsu.structure_matrix_constructor as smc
+    from tnsu.math_objects import spin_operators
+    from tnsu.tensor_network import TensorNetwork
+
+    from conftest import GOLDEN
+
+    smat = smc.rectangular_peps_obc(height=10, width=10)
+    tn = TensorNetwork(structure_matrix=smat, network_name="AFH_10x10_obc_D_4", dir_path=os.path.join(GOLDEN, "networks"),
+                       tensors=None, weights=None)
+    tn.load_network()
+    assert len(tn.tensors) == 100 and tn.tensors[0].dtype == np.complex128 and len(tn.su_logger["error"]) == 396
+    sx, sy, sz = spin_operators(1 / 2)
+    sim = su.SimpleUpdate(tensor_network=tn, dts=[1e-5], j_ij=[1.0] * smat.shape[1], h_k=0.0, s_i=[sx, sy, sz],
+                          s_j=[sx, sy, sz], s_k=[sx], d_max=4, print_process=False)
+    assert abs(sim.energy_per_site() - -0.5616206254235453) < 1e-13
+    # warm start: the stored state is a fixed point of the dt = 1e-5 update up to the run's own tolerance (1e-8)
+    t0, w0 = [np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights]
+    sim.dt = 1e-5
+    sim.simple_update()
+    model = orc.Model([1.0] * smat.shape[1], 0.0, [sx, sy, sz], [sx, sy, sz], [sx])
+    orc.sweep(t0, w0, smat, model, 1e-5, 4)
+    assert max(np.abs(a - b).max() for a, b in zip(w0, tn.weights)) < TOL_W
+    assert sim.compute_convergence_error() < 1e-6
+    e1 = sim.energy_per_site()
+    assert abs(e1 - orc.energy_per_site(t0, w0, smat, model)) < TOL_E
+    with tempfile.TemporaryDirectory() as tmp:
+        tn.dir_path, tn.network_name = tmp, "roundtrip"
+        tn.save_network()
+        tn2 = TensorNetwork(structure_matrix=smat, network_name="roundtrip", dir_path=tmp)
+        tn2.load_network()
+        sim2 = su.SimpleUpdate(tensor_network=tn2, dts=[], j_ij=[1.0] * smat.shape[1], h_k=0.0, s_i=[sx, sy, sz],
+                               s_j=[sx, sy, sz], s_k=[sx])
+        assert abs(sim2.energy_per_site() - e1) < 1e-13
+    capsys.readouterr()
 
 
 def test_known_answer_pickled_state(tnsu):
@@ -386,3 +462,126 @@ def test_engine_error_paths(tnsu):
     with pytest.raises(tnsu.EngineError, match="ARG"):
         eng.set_weights(0, np.ones(3))
     eng.close()
+
+
+def test_inplace_edits_reach_the_device(tnsu):
+    """The reference reads the arrays at call time: an IN-PLACE edit of a tensor or a weight vector between two calls
+    (no list entry replaced) must be seen by the next call (content stamps in SimpleUpdateBatch._state_in_sync)."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("star")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    np.random.seed(4)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=3, spin_dim=2)
+    su = tnsu.SimpleUpdate(tn, [1.0] * 9, 0.1, [sx, sy, sz], [sx, sy, sz], [sz], [0.1], d_max=3, print_process=False)
+    model = orc.Model(su.j_ij, su.h_k, su.s_i, su.s_j, su.s_k)
+
+    def oracle_energy():
+        return orc.energy_per_site([np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights], smat, model)
+
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    tn.tensors[2][0] *= 2.0                       # in place, same array object
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    tn.weights[4][:] = np.array([0.6, 0.3, 0.1])  # in place
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+    su.simple_update()
+    tn.tensors[0] *= 3.0                          # after a download: the arrays handed back are watched too
+    assert abs(su.energy_per_site() - oracle_energy()) < 1e-12
+
+
+def test_nonfinite_state_is_reported_like_the_reference(tnsu):
+    """NaN / Inf in a tensor: scipy's check_finite makes the reference raise ValueError inside simple_update
+    (simple_update.py:243-250); the engine returns TNSU_E_NONFINITE, surfaced as a ValueError subclass, once, and
+    stays usable."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    for dim, poison in ((4, np.nan), (8, np.inf)):
+        np.random.seed(9)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim, spin_dim=2)
+        good = [np.array(t) for t in tn.tensors]
+        su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1], d_max=dim, print_process=False)
+        tn.tensors[1] = tn.tensors[1].copy()
+        tn.tensors[1][0, 1, 0, 2, 1] = poison
+        with pytest.raises(ValueError) as info:
+            su.simple_update()
+        assert isinstance(info.value, tnsu.NonFiniteError) and info.value.code == -4
+        assert su._impl().engine.stats()["nonfinite_events"] == 1
+        for t in range(4):
+            tn.tensors[t] = good[t]
+        tn.weights = [np.ones(dim) / dim for _ in range(8)]
+        su.simple_update()  # healthy state again: no stale error
+        assert all(np.isfinite(w).all() for w in tn.weights) and np.isfinite(su.energy_per_site())
+    # run(): the device loop stops at its next poll
+    np.random.seed(9)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=4, spin_dim=2)
+    tn.tensors[0][1, 0, 0, 0, 0] = np.nan
+    su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1, 0.01], d_max=4, max_iterations=50,
+                           print_process=False)
+    with pytest.raises(ValueError):
+        su.run()
+
+
+def test_jacobi_sweep_limit_is_counted(tnsu, monkeypatch):
+    """A Jacobi iteration that stops at its sweep limit (svd_warp.cuh SVDW_MAX_SWEEPS / 40 in the shared-memory kernel)
+    is counted, not silent: with the limit forced down to 2 sweeps every theta of a random D=8 network hits it."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    for env in ({}, {"TNSU_SVD": "smem"}):
+        for k, v in {"TNSU_SVD_MAX_SWEEPS": "2", **env}.items():
+            monkeypatch.setenv(k, v)
+        np.random.seed(2)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+        su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1], d_max=8, print_process=False)
+        su.simple_update()
+        assert su._impl().engine.stats()["svd_unconverged"] > 0
+        monkeypatch.delenv("TNSU_SVD", raising=False)
+    monkeypatch.delenv("TNSU_SVD_MAX_SWEEPS")
+    np.random.seed(2)
+    tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+    su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1], d_max=8, print_process=False)
+    su.simple_update()
+    assert su._impl().engine.stats()["svd_unconverged"] == 0
+
+
+def test_run_prints_progress_live_and_matches_the_device_loop(tnsu, capsys):
+    """print_process=True drives the loop from the host (live lines with the reference's format, per-dt iteration
+    index, :142-172); the logger equals the device-resident loop's."""
+    smat = tnsu.smc.infinite_structure_matrix_dict("star")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    logs = []
+    for verbose in (True, False):
+        np.random.seed(42)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=2, spin_dim=2)
+        su = tnsu.SimpleUpdate(tn, [1.0] * 9, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1, 0.01], d_max=2, max_iterations=12,
+                               convergence_error=1e-6, log_energy=True, print_process=verbose)
+        su.run()
+        out = capsys.readouterr().out
+        if verbose:
+            lines = [ln for ln in out.splitlines() if ln.startswith("| D max:")]
+            assert len(lines) == len(su.logger["error"]) == 10
+            assert "| iteration:     2/   12 |" in lines[0] and "| dt: 0.010000 |" in lines[-1]
+        logs.append((su.logger, su.dt, su.converged, [np.array(w) for w in tn.weights]))
+    assert logs[0][0]["iteration"] == logs[1][0]["iteration"] and logs[0][1] == logs[1][1] == 0.01
+    assert np.abs(np.array(logs[0][0]["error"]) - np.array(logs[1][0]["error"])).max() < 1e-13
+    assert np.abs(np.array(logs[0][0]["energy"]) - np.array(logs[1][0]["energy"])).max() < 1e-13
+    assert max(np.abs(a - b).max() for a, b in zip(logs[0][3], logs[1][3])) < 1e-13
+
+
+def test_engines_on_two_devices_in_one_process(tnsu):
+    """Shared-memory opt-in is per device and every ABI call restores the caller's current device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    sx, sy, sz = tnsu.spin_operators(0.5)
+    res = []
+    torch.cuda.set_device(0)
+    for dev in (0, 1):
+        np.random.seed(5)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=8, spin_dim=2)
+        su = tnsu.SimpleUpdate(tn, [1.0] * 8, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.1], d_max=8, print_process=False, device=dev)
+        su.dt = 0.1
+        su.simple_update()
+        su.simple_update()
+        res.append(([np.array(w) for w in tn.weights], su.energy_per_site()))
+        assert torch.cuda.current_device() == 0
+    assert max(np.abs(a - b).max() for a, b in zip(res[0][0], res[1][0])) < 1e-13 and abs(res[0][1] - res[1][1]) < 1e-13

@@ -3,7 +3,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, __file__.rsplit("/", 1)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0] + "/tests")
 from conftest import load_golden, unpack_list  # noqa: E402
 
 import tnsu_b200 as tnsu  # noqa: E402

@@ -1,7 +1,7 @@
 """Debug (not a pytest file): do two half-batch engines on two streams overlap K1/K3 with K2?"""
 import sys, time, threading
 import numpy as np
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0])
 import bench  # noqa: E402
 import tnsu_b200 as tnsu  # noqa: E402
 

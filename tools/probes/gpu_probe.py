@@ -1,12 +1,12 @@
 """Verbose GPU parity probe (not a pytest file): prints the deviation of every golden case so one gpurun
-call shows everything at once.  python tests/gpu_probe.py [case ...]"""
+call shows everything at once.  python tools/probes/gpu_probe.py [case ...]"""
 import sys
 import time
 import traceback
 
 import numpy as np
 
-sys.path.insert(0, __file__.rsplit("/", 1)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0] + "/tests")
 from conftest import build_case, load_golden, unpack_list  # noqa: E402
 
 import cases  # noqa: E402

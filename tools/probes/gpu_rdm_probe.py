@@ -1,10 +1,10 @@
 """Debug (not a pytest file): time energy_per_site (pair-RDM kernel) for the DMMA and the staged kernel.
-usage: TNSU_RDM=simple python tests/gpu_rdm_probe.py"""
+usage: TNSU_RDM=simple python tools/probes/gpu_rdm_probe.py"""
 import os
 import sys
 import time
 import numpy as np
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0])
 import bench  # noqa: E402
 import tnsu_b200 as tnsu  # noqa: E402
 

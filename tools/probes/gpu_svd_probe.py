@@ -1,7 +1,7 @@
 """Debug (not a pytest file): Jacobi sweep counts and phase cycles of K2 on bench-like states."""
 import sys
 import numpy as np
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0])
 import bench  # noqa: E402
 import tnsu_b200 as tnsu  # noqa: E402
 

@@ -1,7 +1,7 @@
 """Debug (not a pytest file): host / device phases of the 256-point TFI sweep (bench.py Metric 2)."""
 import sys, time
 import numpy as np
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0])
 import bench  # noqa: F401,E402
 import tnsu_b200 as tnsu  # noqa: E402
 

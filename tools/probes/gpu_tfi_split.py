@@ -1,7 +1,7 @@
 """Debug (not a pytest file): K1/K2/K3 device time per sweep at the TFI D=4 shape, batch 256 and 1."""
 import sys
 import numpy as np
-sys.path.insert(0, __file__.rsplit("/", 2)[0])
+sys.path.insert(0, __file__.rsplit("/", 3)[0])
 import bench  # noqa: F401,E402
 import tnsu_b200 as tnsu  # noqa: E402
 from scipy import linalg
