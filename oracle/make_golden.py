@@ -136,11 +136,17 @@ def run_case(name):
         "oracle_dev_checks": np.array(abs(len(log["error"]) - len(sim.logger["error"]))),
         "oracle_dev_weights": np.array(max(np.abs(a - b).max() for a, b in zip(tn.weights, o_w))),
         "min_weight": np.array(min(float(np.min(w)) for w in tn.weights)),
+        # largest reference-vs-restatement spread along the whole logged trajectory (same number of checks)
+        "oracle_dev_log_energy": np.array(np.abs(np.array(log["energy"]) - np.array(sim.logger["energy"])).max()
+                                          if len(log["energy"]) == len(sim.logger["energy"]) else np.inf),
+        "oracle_dev_log_error": np.array(np.abs(np.array(log["error"]) - np.array(sim.logger["error"])).max()
+                                         if len(log["error"]) == len(sim.logger["error"]) else np.inf),
     }
     _pack_list("weights", tn.weights, store)
     np.savez_compressed(os.path.join(OUT, f"run_{name}.npz"), **store)
     return {"energy": e_ref, "checks": len(sim.logger["error"]), "converged": bool(sim.converged),
-            "dev_e": float(store["oracle_dev_energy"]), "dev_w": float(store["oracle_dev_weights"])}
+            "dev_e": float(store["oracle_dev_energy"]), "dev_w": float(store["oracle_dev_weights"]),
+            "dev_log_e": float(store["oracle_dev_log_energy"]), "dev_log_err": float(store["oracle_dev_log_error"])}
 
 
 def pickled_state():
