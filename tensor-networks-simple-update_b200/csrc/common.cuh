@@ -129,3 +129,14 @@ struct EdgeDesc {
   int Dk, Dnew;  // bond dimension before / after
   int ni, nj;    // theta is (K_i*d) x (d*K_j)
 };
+
+// one site tensor of the network (site RDM kernel, on-chip run kernel)
+struct SiteDesc {
+  void *base;
+  long long point_stride;
+  int nlegs;
+  int dims[TNSU_MAX_LEGS];
+  int leg_edge[TNSU_MAX_LEGS];
+  long long nvirt;  // prod dims
+};
+

@@ -16,6 +16,7 @@
 #include "../../include/tnsu_b200_debug.h"
 #include "edge_update.cuh"
 #include "rdm.cuh"
+#include "run_fused.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -95,6 +96,10 @@ struct tnsu_engine {
   bool force_smem_svd = false;            // TNSU_SVD=smem: keep the shared-memory Jacobi kernel (A/B comparisons)
   std::vector<LevelCfg> cfgs;
   int *d_level_edges = nullptr;
+  int *d_level_off = nullptr;             // [n_levels + 1] (run_fused.cuh)
+  int *d_toff = nullptr;                  // [n] shared-memory offsets of the tensors in the on-chip run kernel
+  bool use_fused = true;                  // TNSU_FUSED=0: never use the on-chip persistent run kernel (A/B comparisons)
+  bool force_fused = false;               // TNSU_FUSED=force: use it for every batch size it fits (A/B comparisons)
   std::vector<int> level_off;
   int *d_all_edges = nullptr;
   SiteDesc *d_site = nullptr;
@@ -724,15 +729,6 @@ static int upload_site_descs(tnsu_engine *e) {
 // ---------------------------------------------------------------------------------------------
 // run-loop state machine (simple_update.py:117-194), one thread per point
 // ---------------------------------------------------------------------------------------------
-struct RunState {
-  int batch, m_edges, n_dts, max_iter, log_cap;
-  double tol;
-  int *slot, *iter, *step, *active, *conv, *nchecks, *log_slot, *log_step, *nactive;
-  const int *is_last;
-  double *log_err, *log_energy;
-  const double *edge_err, *energy;
-};
-
 __global__ void run_state_kernel(RunState s) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.batch || s.active[b] == 0) return;
@@ -792,6 +788,139 @@ __global__ void fill_double_kernel(double *p, long long n, double v) {
   if (i < n) p[i] = v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// on-chip persistent run kernel (run_fused.cuh): eligibility, shared-memory layout, launch
+// ---------------------------------------------------------------------------------------------
+// Returns 1 when the rest of the run was handed to run_fused_kernel, 0 when this network does not qualify (the caller
+// continues with the general launch path), or a negative error code.
+static int try_run_fused(tnsu_engine *e, const RunState &st) {
+  if (!e->use_fused || e->dtype != TNSU_F64 || !e->plan_valid || !e->plan_steady) return 0;
+  int maxnr = 1, maxnc = 1, maxM = 1, maxN = 1, width = 1;
+  for (int ek = 0; ek < e->m; ++ek) {
+    const EdgeDesc &ed = e->h_descs[ek];
+    if (ed.Dnew != ed.Dk) return 0;
+    maxnr = std::max(maxnr, std::max(ed.ni, ed.nj));
+    maxnc = std::max(maxnc, std::min(ed.ni, ed.nj));
+    for (int s = 0; s < 2; ++s) {
+      maxM = std::max(maxM, std::max(ed.s[s].M, ed.s[s].Mout));
+      maxN = std::max(maxN, ed.s[s].N);
+    }
+  }
+  if (maxnr > 32 || maxM > 32 || e->dcap > 32) return 0;
+  for (auto &lv : e->level_edges) width = std::max(width, (int)lv.size());
+  FusedLaunch p{};
+  const int rt[6] = {2, 4, 6, 8, 12, 16};
+  int rows = 16;
+  for (int k = 0; k < 6; ++k)
+    if (rt[k] >= (maxnr + 1) / 2) {
+      rows = rt[k];
+      break;
+    }
+  const int ldm2 = e->ldm * e->ldm;
+  if (e->svd_precond && maxnr >= 8) {
+    // the same geometry as plan_sweep gives svd_warp_kernel: pivoted-QR preconditioner, V-free iteration (measured in this
+    // kernel: the accumulating variant's QR with its Q^T rows costs 46k cycles per 16 x 16 theta against 21k)
+    p.svd_precond = 1;
+    p.svd_np = std::max(1, (maxnr + 1) / 2);
+    p.svd_ldt = std::max(2 * p.svd_np, 2 * rows) | 1;
+    if (e->svd_accumulate_v) return 0;  // TNSU_SVD_V=accumulate (A/B comparisons) stays on the general path
+    {
+      const int tb = rows * p.svd_ldt + 2 * rows + 2, th = 2 * rows * 2 * rows;
+      if (tb <= 2 * ldm2) {
+        p.svd_tb_off = 0;
+        p.svd_group_doubles = 2 * ldm2 + e->d4 + e->dcap + th;
+      } else {
+        p.svd_tb_off = 2 * ldm2 + e->d4 + e->dcap + th;
+        p.svd_group_doubles = p.svd_tb_off + tb;
+      }
+    }
+  } else {
+    if (rows > 4) return 0;  // only thetas below 8 x 8 (or TNSU_SVD_PRECOND=0) go without the preconditioner
+    p.svd_precond = 0;
+    p.svd_accv = 1;
+    p.svd_np = std::max(1, (maxnc + 1) / 2);
+    p.svd_ldt = 0;
+    p.svd_group_doubles = 2 * ldm2 + e->d4 + e->dcap + 2 * rows * 2 * p.svd_np;
+  }
+  p.svd_group_doubles = (p.svd_group_doubles + 1) & ~1;
+  p.svd_max_sweeps = e->svd_max_sweeps;
+  p.ldm = e->ldm;
+  p.mrows = (maxM + 7) & ~7;
+  p.ldp = maxN | 1;
+  p.warp_doubles = fused_warp_doubles(p.svd_group_doubles, p.ldm, p.mrows, p.ldp);
+  p.n_warps = std::min(FUSED_MAX_WARPS, width);
+  std::vector<int> toff(e->n);
+  long long total = 0;
+  for (int t = 0; t < e->n; ++t) {
+    toff[t] = (int)total;
+    total += (tnsu_tensor_elems(e, t) + 1) & ~1LL;
+    if (total > (1 << 20)) return 0;
+  }
+  p.tens_doubles = (int)total;
+  long long smem = 8LL * (total + 2LL * e->m * e->dcap + e->n + 2LL * e->m + 8 + (long long)p.n_warps * p.warp_doubles);
+  if (smem > SMEM_LIMIT - 1024) return 0;
+  if ((long long)e->m * sizeof(EdgeDesc) <= 16384 && smem + (long long)e->m * sizeof(EdgeDesc) <= SMEM_LIMIT - 1024) {
+    p.descs_in_smem = 1;
+    smem += (long long)e->m * sizeof(EdgeDesc);
+  }
+  // The kernel is built for latency: one warp per edge, a few CTAs per SM.  It wins while the batch is at most about one
+  // and a half waves of resident CTAs (measured at the config-3 shape, 4 CTAs x 148 SMs: 0.34 s against 0.42 s of the
+  // launch chain at 256 points, equal at 1024, 1.9 k against 2.2 k points/s at 2048); larger batches keep the
+  // general kernels, which are built for throughput.
+  {
+    int per_sm = 0;
+    cudaError_t co = launch_run_fused_dispatch(p, rows, maxM, maxN, (int)smem, e->stream, true, &per_sm);
+    if (co != cudaSuccess) return fail(e, TNSU_E_CUDA, "on-chip run kernel (occupancy query): %s", cudaGetErrorString(co));
+    if (per_sm < 1) return 0;
+    if (!e->force_fused && 2LL * e->batch > 3LL * per_sm * e->num_sms) return 0;
+  }
+  int rc = upload_site_descs(e);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->d_toff, toff.data(), sizeof(int) * e->n, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // toff is a local
+  p.descs = e->d_descs;
+  p.sites = e->d_site;
+  p.level_edges = e->d_level_edges;
+  p.level_off = e->d_level_off;
+  p.toff = e->d_toff;
+  p.n_levels = (int)e->level_edges.size();
+  p.batch = e->batch;
+  p.m_edges = e->m;
+  p.n_tensors = e->n;
+  p.dcap = e->dcap;
+  p.d4 = e->d4;
+  p.d = e->d;
+  p.weights = e->weights;
+  p.tscale = e->tscale;
+  p.edge_err = e->edge_err;
+  p.energy = e->energy;
+  p.gates = (const double *)e->gates;
+  p.gate_slot_stride = (long long)e->batch * e->m * e->d4;
+  p.hams = (const double *)e->hams;
+  p.rs = st;
+  p.status = e->d_status;
+  long long *d_prof = nullptr;
+  if (getenv("TNSU_FUSED_PROFILE") != nullptr) {
+    CK(cudaMalloc(&d_prof, 96 * sizeof(long long)));
+    CK(cudaMemset(d_prof, 0, 96 * sizeof(long long)));
+    p.prof = d_prof;
+  }
+  cudaError_t ce = launch_run_fused_dispatch(p, rows, maxM, maxN, (int)smem, e->stream, false, nullptr);
+  if (d_prof != nullptr && ce == cudaSuccess) {
+    long long h[16];
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    fprintf(stderr, "[tnsu fused profile] point 0 warp 0, %lld sweeps: cycles stage %lld  lq %lld  svd %lld  recompose %lld  energy %lld  "
+            "level barriers %lld | warps %d smem %lld B rows %d np %d | last SVD: sweeps %d theta+QR %d jacobi %d extract %d\n", h[7], h[0], h[1], h[2], h[3], h[4], h[5], p.n_warps, smem, rows, p.svd_np,
+            ((int *)(h + 8))[7], ((int *)(h + 8))[8], ((int *)(h + 8))[9], ((int *)(h + 8))[10]);
+  }
+  if (ce != cudaSuccess) return fail(e, TNSU_E_CUDA, "on-chip run kernel (rows=%d smem=%lld): %s", rows, smem, cudaGetErrorString(ce));
+  e->launches++;
+  e->fused_runs++;
+  return 1;
+}
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -836,7 +965,7 @@ int tnsu_destroy(tnsu_engine *e) {
                   e->rdm_buf, e->site_buf, e->d_descs, e->d_level_edges, e->d_all_edges, e->d_site, e->r_slot,
                   e->r_iter, e->r_step, e->r_active, e->r_conv, e->r_nchecks, e->r_log_slot, e->r_log_step,
                   e->r_nactive, e->r_islast, e->r_log_err, e->r_log_energy, e->dbg_sigma,
-                  e->dbg_info};
+                  e->dbg_info, e->d_level_off, e->d_toff};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
@@ -919,6 +1048,9 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     e->lqc_force_fallback = env && std::string(env) == "fallback";
     e->lqc_cta_kernel = env && std::string(env) == "cta";
+    env = getenv("TNSU_FUSED");
+    if (env && std::string(env) == "0") e->use_fused = false;
+    if (env && std::string(env) == "force") e->force_fused = true;
     env = getenv("TNSU_SVD_MAX_SWEEPS");
     if (env && atoi(env) > 0) e->svd_max_sweeps = atoi(env);
     env = getenv("TNSU_RC");
@@ -1049,6 +1181,11 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     }
     CKC(cudaMalloc(&e->d_level_edges, sizeof(int) * m));
     CKC(cudaMemcpy(e->d_level_edges, flat.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+    std::vector<int> loff = e->level_off;
+    loff.push_back(m);
+    CKC(cudaMalloc(&e->d_level_off, sizeof(int) * loff.size()));
+    CKC(cudaMemcpy(e->d_level_off, loff.data(), sizeof(int) * loff.size(), cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&e->d_toff, sizeof(int) * n));
     std::vector<int> all(m);
     for (int i = 0; i < m; ++i) all[i] = i;
     CKC(cudaMalloc(&e->d_all_edges, sizeof(int) * m));
@@ -1487,7 +1624,26 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
     return TNSU_OK;
   };
   int rc_loop = TNSU_OK;
+  bool fused_tried = false;
   for (long long it = 0; it < max_global && any; ++it) {
+    // small networks with steady bond dimensions: the rest of the run goes to ONE persistent kernel that keeps each
+    // network in shared memory (run_fused.cuh); the sweeps before (bond growth) ran through the general kernels above
+    if (!e->plan_valid) {
+      rc_loop = plan_sweep(e);
+      if (rc_loop != TNSU_OK) break;
+    }
+    if (gexec == nullptr && fused_tried == false && e->plan_steady) {
+      fused_tried = true;  // eligibility cannot change once the bond dimensions are steady
+      const int fr = try_run_fused(e, st);
+      if (fr < 0) {
+        rc_loop = fr;
+        break;
+      }
+      if (fr == 1) {
+        rc_loop = poll_status(e);
+        break;
+      }
+    }
     if (e->use_graphs && gexec == nullptr && it >= 3 && e->plan_valid && e->plan_steady) {
       const int64_t l0 = e->launches;
       if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

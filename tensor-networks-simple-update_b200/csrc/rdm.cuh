@@ -594,15 +594,6 @@ __global__ void pair_sum_kernel(const cplx *pair_val, int batch, int m_edges, in
 // one-site RDM: rho[s,s'] = sum_x T[s,x] conj(T[s',x]) prod_m lam_m[x_m]^2, trace-normalised.
 // One CTA per (point, tensor).
 // ---------------------------------------------------------------------------------------------
-struct SiteDesc {
-  void *base;
-  long long point_stride;
-  int nlegs;
-  int dims[TNSU_MAX_LEGS];
-  int leg_edge[TNSU_MAX_LEGS];
-  long long nvirt;  // prod dims
-};
-
 template <typename S>
 __global__ void __launch_bounds__(RDM_THREADS) site_rdm_kernel(const SiteDesc *descs, int n_tensors, int d, int batch,
                                                                int m_edges, int dcap, const double *weights,

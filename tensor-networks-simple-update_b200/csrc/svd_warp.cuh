@@ -127,6 +127,26 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
   return rot;
 }
 
+// Everything one call of the warp SVD needs.  The edge-update kernel K2 (svd_warp_kernel) fills it per (point, edge)
+// from global memory; the on-chip run kernel (run_fused.cuh) points it at shared memory.
+struct SvdwArgs {
+  int NP;           // processors (column pairs) per theta; a theta occupies 2 * NP lanes
+  int n_groups;     // thetas per warp handled by this call (lanes beyond n_groups * 2 * NP are surplus)
+  bool valid;       // this lane's group has a theta to factor
+  int d, Dk, Dnew, Ki, Kj, ni, nj, Mi, Mj;
+  double *gs;       // the group's work memory: L_i | L_j | gate | lam_old | theta (| transpose buffer | pivot column)
+  int ldm, dcap, d4, precond, ldt, tb_off, max_sweeps;
+  const double *src_li, *src_lj;  // L factors [M][ldm] (may equal gs / gs + ldm*ldm: then nothing is copied)
+  const double *gate_src;         // d^4 gate of this (point, edge, time step)
+  double *lam;       // the edge's weight vector: old values in, lambda' = s / sum(s) out   (reference :296)
+  double *edge_err;  // || lambda' - lambda ||_2 of this edge (reference :196-206), NaN when the bond dimension changed
+  double *rt_i, *rt_j;  // r~_i, r~_j [d * Dnew][ldm]
+  int *status;       // failure counters (EdgeLaunch::status)
+  int theta_ready;   // the caller has loaded lam_old and built theta in the group memory already (run_fused.cuh)
+  double *dbg_sigma;
+  int *dbg_info;     // nullptr unless this theta is the one tnsu_debug_edge asked for
+};
+
 // ACCV = true: the right rotations are accumulated in registers next to A (rows [A; V]).
 // ACCV = false (needs the QR preconditioner): only A is iterated — 36 % fewer flops, half the shuffles, half the
 // registers — and the Dnew right singular vectors that are kept are recovered at the end from the theta that
@@ -135,78 +155,51 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
 // lambda_k = sigma_k / sum(sigma), so weights / RDMs / energies keep the 1e-10 parity (checked on all golden cases
 // and on product states with weights down to 1e-16 with a numpy model of this route before it was written);
 // vectors of (numerically) zero singular values become an arbitrary orthonormal completion, as they are in LAPACK.
+// Warp-collective: every lane of the warp must call it (lanes without work pass valid = false).
 template <int R, bool ACCV>
-__global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? ((R > 12) ? 3 : ((R > 6) ? 4 : 6)) : ((R > 8) ? 4 : 6)))
-    svd_warp_kernel(const EdgeLaunch<double> p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+DEV void svdw_body(const SvdwArgs &args) {
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int NP = p.svdw_np;
+  const int NP = args.NP;
   const int G = 2 * NP;
-  const int gpw = 32 / G;  // groups per warp
+  const int gpw = args.n_groups;
   const int grp = lane / G;
   const int gl = lane - grp * G;
   const int k = gl >> 1, h = gl & 1;
-  const int n_items = p.batch * p.n_level_edges;
-  const int item = (blockIdx.x * (SVDW_THREADS / 32) + warp) * gpw + grp;
-  bool valid = (grp < gpw) && (item < n_items);
-  int b = 0, ek = 0;
-  if (valid) {
-    b = item / p.n_level_edges;
-    ek = p.level_edges[item - b * p.n_level_edges];
-    if (p.active != nullptr && p.active[b] == 0) valid = false;
-  }
-  // whole-warp early out (no group of this warp has work)
-  if (!__any_sync(0xffffffffu, valid)) return;
-  const int ldm = p.ldm;
+  const bool valid = args.valid;
+  const int ldm = args.ldm;
   const int lda = 2 * R;
-  const bool precond = p.svdw_precond != 0;
+  const bool precond = args.precond != 0;
 
-  // per-group shared memory: Li | Lj | gate | lam_old | theta (column-major, lda x 2NP; with the QR
-  // preconditioner also the transpose buffer 2R x ldt and the pivot column)
-  double *gs = (double *)smem_raw + (size_t)(warp * gpw + (grp < gpw ? grp : 0)) * p.svdw_group_doubles;
+  double *gs = args.gs;
   double *Li = gs;
   double *Lj = Li + ldm * ldm;
   double *gate_s = Lj + ldm * ldm;
-  double *lam_old = gate_s + p.d4;
-  double *th = lam_old + p.dcap;
+  double *lam_old = gate_s + args.d4;
+  double *th = lam_old + args.dcap;
 
-  int d = 1, Dk = 1, Dnew = 1, Ki = 1, Kj = 1, nr = 0, nc = 0;
-  bool transposed = false;
-  double *small = nullptr;
-  double *wpoint = nullptr;
-  if (valid) {
-    const EdgeDesc &ed = p.descs[ek];
-    d = ed.d;
-    Dk = ed.Dk;
-    Dnew = ed.Dnew;
-    Ki = ed.s[0].K;
-    Kj = ed.s[1].K;
-    const int ni = ed.ni, nj = ed.nj;
-    // without preconditioner: A = theta or theta^T so that rows >= columns; with it: A' = theta^T always
-    transposed = precond ? true : (ni < nj);
-    nr = transposed ? nj : ni;
-    nc = transposed ? ni : nj;
-    small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
-    wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
-    const double *gLi = small + SM_L0 * ldm * ldm, *gLj = small + SM_L1 * ldm * ldm;
-    const int Mi = ed.s[0].M, Mj = ed.s[1].M;
-    for (int idx = gl; idx < Mi * ldm; idx += G) Li[idx] = gLi[idx];
-    for (int idx = gl; idx < Mj * ldm; idx += G) Lj[idx] = gLj[idx];
-    const int slot = p.point_slot ? p.point_slot[b] : p.fixed_slot;
-    const double *gsrc = p.gates + (size_t)slot * p.gate_slot_stride + ((size_t)b * p.m_edges + ek) * p.d4;
-    for (int idx = gl; idx < p.d4; idx += G) gate_s[idx] = gsrc[idx];
-    for (int x = gl; x < Dk; x += G) lam_old[x] = wpoint[(size_t)ek * p.dcap + x];
+  const int d = args.d, Dk = args.Dk, Dnew = args.Dnew, Ki = args.Ki, Kj = args.Kj;
+  // without preconditioner: A = theta or theta^T so that rows >= columns; with it: A' = theta^T always
+  const bool transposed = precond ? true : (args.ni < args.nj);
+  const int nr = valid ? (transposed ? args.nj : args.ni) : 0;
+  const int nc = valid ? (transposed ? args.ni : args.nj) : 0;
+  double *lamv = args.lam;
+  if (valid && !args.theta_ready) {
+    if (args.src_li != Li)
+      for (int idx = gl; idx < args.Mi * ldm; idx += G) Li[idx] = args.src_li[idx];
+    if (args.src_lj != Lj)
+      for (int idx = gl; idx < args.Mj * ldm; idx += G) Lj[idx] = args.src_lj[idx];
+    for (int idx = gl; idx < args.d4; idx += G) gate_s[idx] = args.gate_src[idx];
+    for (int x = gl; x < Dk; x += G) lam_old[x] = lamv[x];
   }
   if constexpr (!ACCV) {
     // theta stays in shared memory until the end and is read without bounds there: clear the padding
-    if (grp < gpw)
+    if (grp < gpw && !args.theta_ready)
       for (int idx = gl; idx < lda * 2 * R; idx += G) th[idx] = 0.0;
   }
   __syncwarp();
 
   // theta[(qi,i'),(j',qj)] = sum_{i,j,e} L_i[(i,e),qi] lam_e L_j[(j,e),qj] G[i,j,i',j']   (reference :476-483)
-  if (valid) {
+  if (valid && !args.theta_ready) {
     for (int idx = gl; idx < Ki * Kj; idx += G) {
       const int qi = idx / Kj, qj = idx - qi * Kj;
       // rolled over (i, j): straight-line code here would only evict the Jacobi loop of the other warps from the
@@ -271,10 +264,10 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
     // normalised final X columns.  Measured on the oracle's thetas: 13.3 -> 7.0 Jacobi sweeps.
     // One column of A' and of Z = Q^T per lane (rows in registers); the pivot column travels through shared
     // memory (broadcast reads), the pivot search is one redux over packed (norm, lane) keys.
-    const int ldt = p.svdw_ldt;
+    const int ldt = args.ldt;
     // ACCV: th is reused as the 2R x ldt transpose buffer once A' sits in registers.  !ACCV: theta must survive, the
     // (half-size, R x ldt) buffer and the pivot column live at svdw_tb_off (on the dead L_i / L_j when they fit)
-    double *tb = ACCV ? th : gs + p.svdw_tb_off;
+    double *tb = ACCV ? th : gs + args.tb_off;
     double *wbuf = tb + (size_t)(ACCV ? 2 * R : R) * ldt;  // [2R + 1] pivot column and its trailing norm
     constexpr int RZ = ACCV ? 2 * R : 1;
     double A[2 * R], Z[RZ];
@@ -289,7 +282,10 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
     }
     __syncwarp();
     const int nsteps = valid ? min(nr, nc) : 0;
-    const unsigned gmask = in_group ? (G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << base)) : (1u << lane);
+    // surplus lanes (beyond the last group) share ONE mask: a mask per lane would make the warp execute the pivot
+    // search once per distinct mask (measured in the on-chip run kernel: 16 surplus lanes = 17 serialised redux per step)
+    const unsigned all_groups = (gpw * G >= 32) ? 0xffffffffu : ((1u << (gpw * G)) - 1u);
+    const unsigned gmask = in_group ? (G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << base)) : ~all_groups;
     bool done = !cvalid;
     const int max_steps = min(2 * R, G);
 #pragma unroll 1
@@ -452,7 +448,7 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
   const long long clk_b = clock64();
   int sweeps = 0;
   bool jacobi_done = false;
-  const int max_sweeps = min(p.svd_max_sweeps, SVDW_MAX_SWEEPS);
+  const int max_sweeps = min(args.max_sweeps, SVDW_MAX_SWEEPS);
   if constexpr (ACCV) {
     for (; sweeps < max_sweeps; ++sweeps) {
       bool rotated = false;
@@ -546,25 +542,25 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
     const double mine = (sel_x ? sx : 0.0) + (sel_y ? sy : 0.0);
     for (int j = 0; j < NP; ++j) tot += __shfl_sync(0xffffffffu, mine, in_group ? base + 2 * j : lane);
   }
-  if (valid && gl == 0 && !(tot > 0.0 && tot < 1e300)) atomicOr(p.status, 1);  // NaN / Inf in the state (or theta == 0)
-  if (!jacobi_done && lane == 0) atomicAdd(p.status + 1, 1);
+  if (valid && gl == 0 && !(tot > 0.0 && tot < 1e300)) atomicOr(args.status, 1);  // NaN / Inf in the state (or theta == 0)
+  if (!jacobi_done && lane == 0) atomicAdd(args.status + 1, 1);
   // lambda' = s / sum(s)  (reference :296) and this edge's convergence error (:196-206)
   double e2 = 0.0;
   if (sel_x) {
     const double ln = sx / tot;
-    if (h == 0) wpoint[(size_t)ek * p.dcap + rank_x] = ln;
+    if (h == 0) lamv[rank_x] = ln;
     const double df = ln - lam_old[rank_x];
     e2 += df * df;
   }
   if (sel_y) {
     const double ln = sy / tot;
-    if (h == 0) wpoint[(size_t)ek * p.dcap + rank_y] = ln;
+    if (h == 0) lamv[rank_y] = ln;
     const double df = ln - lam_old[rank_y];
     e2 += df * df;
   }
   double err2 = 0.0;
   for (int j = 0; j < NP; ++j) err2 += __shfl_sync(0xffffffffu, e2, in_group ? base + 2 * j : lane);
-  if (valid && gl == 0) p.edge_err[(size_t)b * p.m_edges + ek] = (Dnew == Dk) ? sqrt(err2) : nan("");
+  if (valid && gl == 0) *args.edge_err = (Dnew == Dk) ? sqrt(err2) : nan("");
 
   if constexpr (!ACCV) {
     // ---- right singular vectors of the Dnew columns that are kept, from the theta left in shared memory ----
@@ -582,10 +578,10 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
     // (one column at a time, its r~_i written right away, so that A and W never sit in registers together)
     double wx[R], wy[R];
     const double *thh = th + (size_t)(h * R) * lda;
-    double *wt = gs + p.svdw_tb_off;  // R x ldt, free since the transposition
-    const int ldt_w = p.svdw_ldt;
-    double *rt_i = valid ? small + SM_R0 * ldm * ldm : nullptr;
-    const int n_rowidx = valid ? p.descs[ek].ni : 0;
+    double *wt = gs + args.tb_off;  // R x ldt, free since the transposition
+    const int ldt_w = args.ldt;
+    double *rt_i = valid ? args.rt_i : nullptr;
+    const int n_rowidx = valid ? args.ni : 0;
     // theta-row index (qi, i') of my first row, advanced without divisions
     const int gr0 = h * R;
     const int qi0 = gr0 / d, ip0 = gr0 - qi0 * d;
@@ -695,8 +691,8 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
       }
     }
     if (valid) {
-      double *rt_j = small + SM_R1 * ldm * ldm;
-      const int n_colidx = p.descs[ek].nj;
+      double *rt_j = args.rt_j;
+      const int n_colidx = args.nj;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         const bool sel = which ? sel_y : sel_x;
@@ -718,11 +714,11 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
 
   // r~_i[(i',x'),qi] = U[(qi,i'),x'],   r~_j[(j',x'),qj] = V^T[x',(j',qj)]     (reference :268-271)
   if (valid) {
-    double *rt_i = small + SM_R0 * ldm * ldm, *rt_j = small + SM_R1 * ldm * ldm;
+    double *rt_i = args.rt_i, *rt_j = args.rt_j;
     // which register half carries the theta-ROW-index vector: A/sigma unless A = theta^T was iterated directly;
     // with the preconditioner A' = theta^T but the roles are swapped once more (X = R^T), so it is A/sigma again
     const bool row_is_v = transposed && !precond;
-    const int n_rowidx = p.descs[ek].ni, n_colidx = p.descs[ek].nj;
+    const int n_rowidx = args.ni, n_colidx = args.nj;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       const bool sel = ACCV && (which ? sel_y : sel_x);
@@ -749,27 +745,89 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
         }
       }
     }
-    if (p.dbg_info != nullptr && b == p.dbg_point) {
-      if (sel_x && h == 0) p.dbg_sigma[rank_x] = sx;
-      if (sel_y && h == 0) p.dbg_sigma[rank_y] = sy;
-      if (!sel_x && h == 0 && rank_x < TNSU_MAX_SVD && sx >= 0.0) p.dbg_sigma[rank_x] = sx;
-      if (!sel_y && h == 0 && rank_y < TNSU_MAX_SVD && sy >= 0.0) p.dbg_sigma[rank_y] = sy;
+    if (args.dbg_info != nullptr) {
+      if (sel_x && h == 0) args.dbg_sigma[rank_x] = sx;
+      if (sel_y && h == 0) args.dbg_sigma[rank_y] = sy;
+      if (!sel_x && h == 0 && rank_x < TNSU_MAX_SVD && sx >= 0.0) args.dbg_sigma[rank_x] = sx;
+      if (!sel_y && h == 0 && rank_y < TNSU_MAX_SVD && sy >= 0.0) args.dbg_sigma[rank_y] = sy;
       if (gl == 0) {
-        const EdgeDesc &ed = p.descs[ek];
-        p.dbg_info[0] = ed.s[0].M;
-        p.dbg_info[1] = Ki;
-        p.dbg_info[2] = ed.s[1].M;
-        p.dbg_info[3] = Kj;
-        p.dbg_info[4] = ed.ni;
-        p.dbg_info[5] = ed.nj;
-        p.dbg_info[6] = Dnew;
-        p.dbg_info[7] = sweeps;
-        p.dbg_info[8] = (int)(clk_b - clk_a);   // load / QR preconditioner
-        p.dbg_info[9] = (int)(clk_c - clk_b);   // Jacobi
-        p.dbg_info[10] = (int)(clock64() - clk_c);  // extract
+        args.dbg_info[0] = args.Mi;
+        args.dbg_info[1] = Ki;
+        args.dbg_info[2] = args.Mj;
+        args.dbg_info[3] = Kj;
+        args.dbg_info[4] = args.ni;
+        args.dbg_info[5] = args.nj;
+        args.dbg_info[6] = Dnew;
+        args.dbg_info[7] = sweeps;
+        args.dbg_info[8] = (int)(clk_b - clk_a);   // load / QR preconditioner
+        args.dbg_info[9] = (int)(clk_c - clk_b);   // Jacobi
+        args.dbg_info[10] = (int)(clock64() - clk_c);  // extract
       }
     }
   }
+}
+
+#ifndef RUN_FUSED_IMPL  // the on-chip run kernel's translation unit only needs svdw_body
+template <int R, bool ACCV>
+__global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? ((R > 12) ? 3 : ((R > 6) ? 4 : 6)) : ((R > 8) ? 4 : 6)))
+    svd_warp_kernel(const EdgeLaunch<double> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int G = 2 * p.svdw_np;
+  const int gpw = 32 / G;  // groups per warp
+  const int grp = lane / G;
+  const int n_items = p.batch * p.n_level_edges;
+  const int item = (blockIdx.x * (SVDW_THREADS / 32) + warp) * gpw + grp;
+  bool valid = (grp < gpw) && (item < n_items);
+  int b = 0, ek = 0;
+  if (valid) {
+    b = item / p.n_level_edges;
+    ek = p.level_edges[item - b * p.n_level_edges];
+    if (p.active != nullptr && p.active[b] == 0) valid = false;
+  }
+  // whole-warp early out (no group of this warp has work)
+  if (!__any_sync(0xffffffffu, valid)) return;
+  SvdwArgs a{};
+  a.NP = p.svdw_np;
+  a.n_groups = gpw;
+  a.valid = valid;
+  a.gs = (double *)smem_raw + (size_t)(warp * gpw + (grp < gpw ? grp : 0)) * p.svdw_group_doubles;
+  a.ldm = p.ldm;
+  a.dcap = p.dcap;
+  a.d4 = p.d4;
+  a.precond = p.svdw_precond;
+  a.ldt = p.svdw_ldt;
+  a.tb_off = p.svdw_tb_off;
+  a.max_sweeps = p.svd_max_sweeps;
+  a.status = p.status;
+  if (valid) {
+    const EdgeDesc &ed = p.descs[ek];
+    a.d = ed.d;
+    a.Dk = ed.Dk;
+    a.Dnew = ed.Dnew;
+    a.Ki = ed.s[0].K;
+    a.Kj = ed.s[1].K;
+    a.ni = ed.ni;
+    a.nj = ed.nj;
+    a.Mi = ed.s[0].M;
+    a.Mj = ed.s[1].M;
+    const int ldm2 = p.ldm * p.ldm;
+    double *small = p.small + (size_t)item * SM_COUNT * ldm2;
+    a.src_li = small + SM_L0 * ldm2;
+    a.src_lj = small + SM_L1 * ldm2;
+    a.rt_i = small + SM_R0 * ldm2;
+    a.rt_j = small + SM_R1 * ldm2;
+    const int slot = p.point_slot ? p.point_slot[b] : p.fixed_slot;
+    a.gate_src = p.gates + (size_t)slot * p.gate_slot_stride + ((size_t)b * p.m_edges + ek) * p.d4;
+    a.lam = p.weights + ((size_t)b * p.m_edges + ek) * p.dcap;
+    a.edge_err = p.edge_err + (size_t)b * p.m_edges + ek;
+    if (p.dbg_info != nullptr && b == p.dbg_point) {
+      a.dbg_sigma = p.dbg_sigma;
+      a.dbg_info = p.dbg_info;
+    }
+  }
+  svdw_body<R, ACCV>(a);
 }
 
 template <int R, bool ACCV>
@@ -800,3 +858,4 @@ inline cudaError_t launch_svd_warp(const EdgeLaunch<double> &p, int n_items, cud
   if (r <= 12) return launch_svd_warp_r<12, true>(p, n_items, st);
   return launch_svd_warp_r<16, true>(p, n_items, st);
 }
+#endif  // !RUN_FUSED_IMPL

@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     jobs = [(os.path.join(bdir, "engine.o"), [os.path.join(CSRC, "engine.cu")]),
             (os.path.join(bdir, "svdw_inst.o"), [os.path.join(CSRC, "svdw_inst.cu")]),
             (os.path.join(bdir, "rc_inst.o"), [os.path.join(CSRC, "rc_inst.cu")]),
-            (os.path.join(bdir, "lqc_inst.o"), [os.path.join(CSRC, "lqc_inst.cu")])]
+            (os.path.join(bdir, "lqc_inst.o"), [os.path.join(CSRC, "lqc_inst.cu")]),
+            (os.path.join(bdir, "fused_inst.o"), [os.path.join(CSRC, "fused_inst.cu")])]
     for cx in (0, 1):
         for mm in (8, 16, 32):
             jobs.append((os.path.join(bdir, f"edge_{'c' if cx else 'd'}{mm}.o"),

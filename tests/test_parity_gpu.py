@@ -596,3 +596,51 @@ def test_engines_on_two_devices_in_one_process(tnsu):
         res.append(([np.array(w) for w in tn.weights], su.energy_per_site()))
         assert torch.cuda.current_device() == 0
     assert max(np.abs(a - b).max() for a, b in zip(res[0][0], res[1][0])) < 1e-13 and abs(res[0][1] - res[1][1]) < 1e-13
+
+
+@pytest.mark.parametrize("lattice,d,dim0,d_max,field", [
+    ("peps", 2, 4, 4, -3.0),       # config 3 shape: register-resident variant <8, 8, 2>
+    ("star", 2, 2, 2, 0.0),        # config 1 shape: <4, 8, 1>
+    ("star", 2, 3, 3, 0.3),        # <6, 8, 1>
+    ("peps", 2, 5, 5, 0.0),        # <12, 16, 4>
+    ("peps", 2, 2, 4, 0.2),        # bond growth 2 -> 4 on the general kernels first, then the on-chip kernel
+    ("chain", 2, 8, 8, 0.0),       # M > N bond matrices (K = N): generic shared-memory variant
+    ("kagome_3", 3, 2, 2, 0.1),    # spin 1, d = 3
+    ("cube", 2, 2, 2, 0.0),        # z = 6
+    ("peps", 2, 1, 1, 0.5),        # product state: thetas below 8 x 8 (no preconditioner, accumulating Jacobi)
+])
+def test_on_chip_run_kernel_matches_general_path(tnsu, monkeypatch, lattice, d, dim0, d_max, field):
+    """run() of a small network goes to ONE persistent kernel that keeps the network in shared memory
+    (run_fused.cuh); TNSU_FUSED=0 keeps the general launch path.  Same control flow (checks at the same sweeps, same
+    dt stages, same converged flag), same logs / weights / energies; and both equal the oracle's run()."""
+    smat = tnsu.smc.infinite_structure_matrix_dict(lattice)
+    m = smat.shape[1]
+    sx, sy, sz = tnsu.spin_operators((d - 1) / 2.0)
+    out = []
+    for env in ("0", "1"):
+        monkeypatch.setenv("TNSU_FUSED", env)
+        nets = []
+        for k in range(3):
+            np.random.seed(50 + k)
+            nets.append(tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim0, spin_dim=d))
+        ref = [tn.copy() for tn in nets]
+        batch = tnsu.SimpleUpdateBatch(nets, [1.0] * m, tnsu.per_point([field, field + 0.1, field - 0.2]), [sx, sy, sz],
+                                       [sx, sy, sz], [sz], [0.1, 0.02], d_max=d_max, max_iterations=14, convergence_error=1e-4)
+        logs = batch.run()
+        out.append((logs, batch.energy_per_site(), [np.array(w) for tn in nets for w in tn.weights],
+                    batch.engine.stats()["fused_runs"]))
+    assert out[0][3] == 0 and out[1][3] == 1
+    for la, lb in zip(out[0][0], out[1][0]):
+        assert la["iteration"] == lb["iteration"] and la["dt"] == lb["dt"] and la["converged"] == lb["converged"]
+        assert la["sweeps"] == lb["sweeps"] and la["final_dt"] == lb["final_dt"]
+        assert np.abs(np.array(la["error"]) - np.array(lb["error"])).max() < 1e-11
+        assert np.abs(np.array(la["energy"]) - np.array(lb["energy"])).max() < 1e-11
+    assert np.abs(out[0][1] - out[1][1]).max() < 1e-11
+    assert max(np.abs(a - b).max() for a, b in zip(out[0][2], out[1][2])) < 1e-11
+    # and against the oracle (reference :107-194) for the first point
+    model = orc.Model([1.0] * m, field, [sx, sy, sz], [sx, sy, sz], [sz])
+    t, w = [np.array(x) for x in ref[0].tensors], [np.array(x) for x in ref[0].weights]
+    log = orc.run(t, w, smat, model, [0.1, 0.02], d_max, 14, 1e-4)
+    assert log["iteration"] == out[1][0][0]["iteration"] and log["converged"] == out[1][0][0]["converged"]
+    assert np.abs(np.array(log["error"]) - np.array(out[1][0][0]["error"])).max() < 1e-10
+    assert np.abs(np.array(log["energy"]) - np.array(out[1][0][0]["energy"])).max() < 1e-10
