@@ -166,11 +166,17 @@ constexpr int edge_max_threads() {
 // =============================================================================================
 // K1: absorb + Householder LQ + compact-WY factors
 // =============================================================================================
-template <typename S, int MMAX, int NCOLS>
+// CLUSTER = true (wide bond matrices, complex128: the real path has its own cluster variant in lq_rolled_kernel): the
+// columns of one (item, side) are split over the p.cluster CTAs of a thread-block cluster; each step's partial Gram row
+// goes to the CTA's shared memory, one cluster.sync(), every CTA sums the peers' rows through distributed shared memory
+// and reads the pivot column from the first CTA.
+template <typename S, int MMAX, int NCOLS, bool CLUSTER = false>
 __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kernel(const EdgeLaunch<S> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int item = blockIdx.x >> 1;
-  const int side = blockIdx.x & 1;
+  const int CL = CLUSTER ? p.cluster : 1;
+  const int rank = CLUSTER ? (int)(blockIdx.x % CL) : 0;
+  const int item = (int)(blockIdx.x / CL) >> 1;
+  const int side = (int)(blockIdx.x / CL) & 1;
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
@@ -197,6 +203,10 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   S *matT = matZ + ldm * ldm;                                         // T (K x K)
   S *matY = matT + ldm * ldm;                                         // first K columns of Y^H
   double *tau_s = (double *)(matY + ldm * ldm);                       // [MMAX]
+  S *cpart = (S *)(smem_raw + p.lq_stage_off);                        // [2][MMAX] this CTA's partial Gram row (CLUSTER)
+  const int ncl = (N + CL - 1) / CL;                                   // columns per CTA of the cluster
+  const int c0 = rank * ncl;
+  const int c_end = min(N, c0 + ncl);
 
   const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
   for (int idx = lt; idx < sd.nlegs * p.dcap; idx += nt) {
@@ -216,9 +226,9 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   S col[NCOLS][MMAX];
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const int c = lt + j * nt;
-    const ColInfo ci = decode_column(sd, c, wleg, p.dcap);
-    const bool valid = c < N;
+    const int c = c0 + lt + j * nt;
+    const bool valid = c < c_end;
+    const ColInfo ci = decode_column(sd, valid ? c : 0, wleg, p.dcap);
     const double wc = ci.w * tsc;
 #pragma unroll
     for (int r = 0; r < MMAX; ++r) {
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
       constexpr int buf = kk & 1;
 #pragma unroll
       for (int j = 0; j < NCOLS; ++j) {
-        if (lt + j * nt == kk) {
+        if (c0 + lt + j * nt == kk) {
 #pragma unroll
           for (int i = 0; i < MMAX; ++i) colk[buf * MMAX + i] = col[j][i];
         }
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
           for (int i = 0; i < CH; ++i) acc[i] = from_real<S>(0.0);
 #pragma unroll
           for (int j = 0; j < NCOLS; ++j) {
-            if (lt + j * nt > kk) {
+            if (c0 + lt + j * nt > kk) {
               const S pk = cj(col[j][kk]);
 #pragma unroll
               for (int i = 0; i < CH; ++i) fma_acc(acc[i], col[j][cb + i], pk);
@@ -266,9 +276,21 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
       S mycol = from_real<S>(0.0);
       if (lane < M) {
         for (int w = 0; w < nwarps; ++w) g = g + red[(buf * TNSU_MAX_WARPS + w) * MMAX + lane];
-        mycol = colk[buf * MMAX + lane];
       }
-      const S alpha = colk[buf * MMAX + kk];
+      const S *colk_src = colk;
+      if constexpr (CLUSTER) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (wl == 0 && lane < MMAX) cpart[buf * MMAX + lane] = g;
+        cluster.sync();
+        S tot = from_real<S>(0.0);
+        if (lane < M)
+          for (int r = 0; r < CL; ++r) tot = tot + cluster.map_shared_rank(cpart, r)[buf * MMAX + lane];
+        g = tot;
+        colk_src = cluster.map_shared_rank(colk, 0);
+      }
+      if (lane < M) mycol = colk_src[buf * MMAX + lane];
+      const S alpha = colk_src[buf * MMAX + kk];
       const double gk = re(shfl_idx(g, kk));
       const double a2 = abs2(alpha);
       const double norm2 = gk + a2;
@@ -301,12 +323,12 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
         const S wi = shfl_idx(w_l, i);
 #pragma unroll
         for (int j = 0; j < NCOLS; ++j) {
-          if (lt + j * nt > kk) fms_acc(col[j][i], wi, col[j][kk]);
+          if (c0 + lt + j * nt > kk) fms_acc(col[j][i], wi, col[j][kk]);
         }
       }
 #pragma unroll
       for (int j = 0; j < NCOLS; ++j) {
-        const int c = lt + j * nt;
+        const int c = c0 + lt + j * nt;
         if (c == kk)
           col[j][kk] = head;
         else if (c < kk)
@@ -319,8 +341,8 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   S *ybase = (S *)sd.ybase + (size_t)b * sd.point_stride;
 #pragma unroll
   for (int j = 0; j < NCOLS; ++j) {
-    const int c = lt + j * nt;
-    if (c < N) {
+    const int c = c0 + lt + j * nt;
+    if (c < c_end) {
 #pragma unroll
       for (int k = 0; k < MMAX; ++k)
         if (k < K) ybase[(size_t)k * N + c] = col[j][k];
@@ -332,6 +354,11 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
     }
   }
   __syncthreads();
+  if constexpr (CLUSTER) {
+    // no CTA may leave while a peer can still read its shared memory; only the first CTA writes L and S
+    cooperative_groups::this_cluster().sync();
+    if (rank != 0) return;
+  }
 
   // compact-WY factor: T[:k,k] = -tau_k T[:k,:k] Z[:k,k], T[k,k] = tau_k   (lane r holds row r)
   if (wl == 0) {
@@ -1236,6 +1263,25 @@ template <typename S, int MM, int NC>
 cudaError_t launch_lq_variant(const EdgeLaunch<S> &p, int n_items, cudaStream_t st) {
   if constexpr (std::is_same<S, double>::value) {
     if (p.lq_rolled) return launch_lq_rolled<MM, NC>(p, n_items, st);
+  }
+  if constexpr (!std::is_same<S, double>::value) {
+    if (p.cluster > 1) {
+      auto kernc = lq_kernel<S, MM, NC, true>;
+      if (cudaError_t s = tnsu_opt_in_smem((const void *)kernc); s != cudaSuccess) return s;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2u * n_items * p.cluster);
+      cfg.blockDim = dim3(p.nt);
+      cfg.dynamicSmemBytes = p.smem_lq;
+      cfg.stream = st;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = p.cluster;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kernc, p);
+    }
   }
   auto kern = lq_kernel<S, MM, NC>;
   if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;

@@ -286,12 +286,13 @@ static int plan_sweep(tnsu_engine *e) {
       c.nt = nt;
       ok = true;
     }
-    if (!ok && !cx && !e->force_unrolled_lq) {
+    if (!ok && !(e->force_unrolled_lq && !cx)) {
       // wide bond matrices: split the columns over a thread-block cluster of 2, 4 or 8 CTAs (K1) / column slices (K3)
       for (int cl = 2; cl <= 8 && !ok; cl *= 2) {
         const int ncl = (maxN + cl - 1) / cl;
         for (int o = 0; o < 2 && !ok; ++o) {
           const int nc = order2[o];
+          if (cx && c.mm_t == 32 && nc == 2) continue;  // not instantiated
           const int nt = ((ncl + nc - 1) / nc + 31) & ~31;
           if (nt > max_threads(cx, c.mm_t, nc) || nt > TNSU_MAX_WARPS * 32) continue;
           c.ncols = nc;
@@ -314,7 +315,7 @@ static int plan_sweep(tnsu_engine *e) {
     if (!cx) c.smem_lq += (c.nt / 32) * c.mm_t * 33 * 8;  // per-warp transpose buffers of lq_rolled_kernel
     if (c.cluster > 1) {
       c.lq_stage_off = (c.smem_lq + 15) & ~15;  // the cluster's partial Gram rows [2][MMAX]
-      c.smem_lq = c.lq_stage_off + 2 * c.mm_t * 8 + 16;
+      c.smem_lq = c.lq_stage_off + 2 * c.mm_t * ssz + 16;
     }
     if (!cx && e->lq_stream && c.cluster == 1) {
       // streaming K1: one staging buffer for the largest site tensor of the level; two CTAs must fit one SM

@@ -229,8 +229,11 @@ def test_reference_experiments(tnsu, capsys, lattice, d_max, j, h, field, expect
     assert all(len(w) <= d_max for w in tn.weights)
 
 
-@pytest.mark.parametrize("lattice,dim,d", [("peps", 10, 2), ("peps", 12, 2), ("peps", 16, 2), ("triangle", 5, 2), ("chain", 16, 2), ("star", 12, 2), ("peps", 5, 3)])
-def test_large_shapes_match_oracle(tnsu, lattice, dim, d):
+@pytest.mark.parametrize("lattice,dim,d,cplx_init", [("peps", 10, 2, False), ("peps", 12, 2, False), ("peps", 16, 2, False),
+                                                   ("triangle", 5, 2, False), ("chain", 16, 2, False), ("star", 12, 2, False),
+                                                   ("peps", 5, 3, False), ("peps", 10, 2, True), ("peps", 12, 2, True),
+                                                   ("star", 16, 2, True), ("chain", 16, 2, True)])
+def test_large_shapes_match_oracle(tnsu, lattice, dim, d, cplx_init):
     """Shapes beyond the BASELINE configs, up to what the kernels keep on chip (d*D = 32 rows; up to 1024 columns in
     one CTA, up to 8 x 512 in a thread-block cluster): two sweeps against the oracle on the same seeded input."""
     smat = tnsu.smc.infinite_structure_matrix_dict(lattice)
@@ -238,6 +241,8 @@ def test_large_shapes_match_oracle(tnsu, lattice, dim, d):
     m = smat.shape[1]
     np.random.seed(21)
     tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim, spin_dim=d)
+    if cplx_init:  # complex128 engine: wide bond matrices go through the thread-block-cluster Householder kernel too
+        tn.tensors = [t + 1j * np.random.normal(size=t.shape) for t in tn.tensors]
     t0, w0 = [np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights]
     su = tnsu.SimpleUpdate(tn, [1.0] * m, 0.0, [sx, sy, sz], [sx, sy, sz], [], [0.05], d_max=dim, print_process=False)
     su.dt = 0.05
