@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
+  // behind the streaming CholeskyQR2 kernel (lq_chol.cuh): only the (item, side)s it flagged are factored here
+  if (p.lq_flags != nullptr) {
+    if (p.lq_flags[blockIdx.x / CL] == 0) return;
+    if (p.lq_stats != nullptr && threadIdx.x == 0 && rank == 0) atomicAdd(p.lq_stats, 1);
+  }
 
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
@@ -966,8 +971,11 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
   S *Lj = Li + ldm * ldm;
   S *gate_s = Lj + ldm * ldm;
   S *svdA = gate_s + p.d4;
-  S *svdV = svdA + (size_t)p.lda * p.ldv;  // nc <= ldv columns
-  double *sig = (double *)(svdV + (size_t)p.ldv * p.ldv);
+  // V (nc x nc) overlays L_i | L_j, which are dead once theta is built, whenever it fits there (a third less shared
+  // memory per theta: 4 instead of 3 resident CTAs per SM at 32 x 32 complex128)
+  const bool v_on_l = (size_t)p.ldv * p.ldv <= (size_t)2 * ldm * ldm;
+  S *svdV = v_on_l ? Li : svdA + (size_t)p.lda * p.ldv;  // nc <= ldv columns
+  double *sig = (double *)(svdA + (size_t)p.lda * p.ldv + (v_on_l ? 0 : (size_t)p.ldv * p.ldv));
   double *lam_old = sig + TNSU_MAX_SVD;
   int *order = (int *)(lam_old + TNSU_MAX_SVD);
   int *flag = order + TNSU_MAX_SVD;
@@ -1018,6 +1026,7 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
       }
   }
   long long clk1 = clock64();
+  __syncthreads();  // every read of L_i / L_j is done before V is initialised on top of them
   const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40));
   long long clk2 = clock64();
 
@@ -1103,6 +1112,7 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
   const int b = item / p.n_level_edges;
   const int ek = p.level_edges[item - b * p.n_level_edges];
   if (p.active != nullptr && p.active[b] == 0) return;
+  if (p.lq_flags != nullptr && p.lq_flags[blockIdx.x / CL] == 0) return;  // recomposed by recompose_chol_kernel
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &sd = ed.s[side];
   const int nt = blockDim.x;

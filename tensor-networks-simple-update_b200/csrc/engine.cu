@@ -332,7 +332,8 @@ static int plan_sweep(tnsu_engine *e) {
         c.lq_stream_grid = 2 * e->num_sms;
       }
     }
-    c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + c.ldv * c.ldv) * ssz + 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
+    c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv)) * ssz + 2 * TNSU_MAX_SVD * 8 +
+                 TNSU_MAX_SVD * 4 + 64;
     c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
     // real thetas of at most 32 x 32 take the register-resident warp kernel (svd_warp.cuh)
     if (!cx && maxnr <= 32 && !e->force_smem_svd) {
@@ -368,8 +369,8 @@ static int plan_sweep(tnsu_engine *e) {
       }
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
-    if (!cx && !e->force_householder && !e->force_simple_rc && !e->lq_stream && !e->force_unrolled_lq && e->dcap <= 32 &&
-        c.cluster == 1 && maxN >= 256) {
+    if (!e->force_householder && !e->force_simple_rc && !e->lq_stream && !e->force_unrolled_lq && e->dcap <= 32 &&
+        (cx ? 2 * maxM <= 32 : c.cluster == 1) && maxN >= 256) {
       // streaming K1/K3: every side of the level must have M <= N, an unchanged bond dimension (the recompose runs in
       // place) and tensors below 2 GiB (32-bit byte offsets).  Narrow bond matrices (N < 256: the D <= 4 networks of the
       // sweep metric) stay with the Householder kernels: there a launch is latency bound, and two Cholesky chains plus
@@ -382,7 +383,7 @@ static int plan_sweep(tnsu_engine *e) {
         for (int s2 = 0; s2 < 2; ++s2) {
           const SideDesc &sd2 = ed.s[s2];
           if (sd2.M > sd2.N || sd2.Mout != sd2.M) ok_lqc = false;
-          if ((long long)sd2.M * sd2.N * 8 >= (1LL << 31)) ok_lqc = false;
+          if ((long long)sd2.M * sd2.N * ssz >= (1LL << 31)) ok_lqc = false;
           for (int l = 0; l < sd2.nlegs; ++l)
             if (sd2.in_stride[l] != sd2.out_stride[l]) ok_lqc = false;
           if (sd2.in_stride_phys != sd2.out_stride_phys) ok_lqc = false;
@@ -477,6 +478,12 @@ static cudaError_t launch_side_kernel(bool recompose, const LevelCfg &c, const E
 cudaError_t launch_svd_warp_dispatch(const EdgeLaunch<double> &p, int n_items, cudaStream_t st);  // svdw_inst.cu
 cudaError_t launch_lq_chol_dispatch(const EdgeLaunch<double> &p, int n_items, int m_max, int *flags, cudaStream_t st);  // lqc_inst.cu
 cudaError_t launch_rc_chol_dispatch(const EdgeLaunch<double> &p, int n_items, int m_max, const int *flags, cudaStream_t st);
+cudaError_t launch_lq_chol_cx_dispatch(const EdgeLaunch<cplx> &p, int n_items, int m_max, int *flags, cudaStream_t st);
+cudaError_t launch_rc_chol_cx_dispatch(const EdgeLaunch<cplx> &p, int n_items, int m_max, const int *flags, cudaStream_t st);
+static cudaError_t launch_k1c(const EdgeLaunch<double> &p, int n, int m, int *f, cudaStream_t st) { return launch_lq_chol_dispatch(p, n, m, f, st); }
+static cudaError_t launch_k1c(const EdgeLaunch<cplx> &p, int n, int m, int *f, cudaStream_t st) { return launch_lq_chol_cx_dispatch(p, n, m, f, st); }
+static cudaError_t launch_k3c(const EdgeLaunch<double> &p, int n, int m, const int *f, cudaStream_t st) { return launch_rc_chol_dispatch(p, n, m, f, st); }
+static cudaError_t launch_k3c(const EdgeLaunch<cplx> &p, int n, int m, const int *f, cudaStream_t st) { return launch_rc_chol_cx_dispatch(p, n, m, f, st); }
 cudaError_t launch_recompose_dmma_dispatch(const EdgeLaunch<double> &p, int n_items, int mout_max, int k_max, int ncl_cap,
                                            cudaStream_t st);  // rc_inst.cu
 
@@ -561,27 +568,23 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     cudaError_t st = cudaSuccess;
     if (e->profile) cudaEventRecord(e->pev[0], e->stream);
     int extra_launches = 0;
-    if constexpr (sizeof(S) == 8) {
-      if (c.lqc && only_edge < 0 && e->run_sweep_index >= e->lqc_suspend_until) {
-        // streaming CholeskyQR2 first; it flags the (item, side)s it cannot take and the Householder kernels below
-        // then process exactly those (every other CTA of theirs returns at once)
-        p.lq_flags = e->lq_flags;
-        p.lq_stats = e->lq_stats;
-        e->lqc_attempted += 2LL * n_items;
-        e->lqc_attempted_total += 2LL * n_items;
-        st = launch_lq_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
-        ++extra_launches;
-      }
+    if (c.lqc && only_edge < 0 && e->run_sweep_index >= e->lqc_suspend_until) {
+      // streaming CholeskyQR2 first; it flags the (item, side)s it cannot take and the Householder kernels below
+      // then process exactly those (every other CTA of theirs returns at once)
+      p.lq_flags = e->lq_flags;
+      p.lq_stats = e->lq_stats;
+      e->lqc_attempted += 2LL * n_items;
+      e->lqc_attempted_total += 2LL * n_items;
+      st = launch_k1c(p, n_items, c.lqc_m, e->lq_flags, e->stream);
+      ++extra_launches;
     }
     if (st == cudaSuccess) st = launch_side_kernel<S>(false, c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[1], e->stream);
     if (st == cudaSuccess) st = launch_k2<S>(c, p, n_items, e->stream);
     if (e->profile) cudaEventRecord(e->pev[2], e->stream);
-    if constexpr (sizeof(S) == 8) {
-      if (st == cudaSuccess && p.lq_flags != nullptr) {
-        st = launch_rc_chol_dispatch(p, n_items, c.lqc_m, e->lq_flags, e->stream);
-        ++extra_launches;
-      }
+    if (st == cudaSuccess && p.lq_flags != nullptr) {
+      st = launch_k3c(p, n_items, c.lqc_m, e->lq_flags, e->stream);
+      ++extra_launches;
     }
     if (st == cudaSuccess) st = launch_k3<S>(c, p, n_items, e->stream);
     if (e->profile) {

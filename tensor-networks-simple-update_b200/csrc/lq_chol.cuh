@@ -99,6 +99,59 @@ DEV void lqc_tri_inverse(const double (&l)[MP], double invd, double (&x)[MP], in
   }
 }
 
+
+// ---- complex128 versions (lane = complex row, MC = MP / 2 complex rows): the Gram matrix arrives as the real 2M x 2M Gram
+// of the row-interleaved (re, im) matrix, G[r][c] = (g[2r][2c] + g[2r+1][2c+1]) + i (g[2r+1][2c] - g[2r][2c+1]) ----
+template <int MC>
+DEV bool lqc_cholesky_cx(double (&gre)[MC], double (&gim)[MC], double (&lre)[MC], double (&lim)[MC], double &invd, int lane, int M) {
+  bool ok = true;
+  double dmin = 1e300, dmax = 0.0;
+  invd = 1.0;
+#pragma unroll
+  for (int k = 0; k < MC; ++k) {
+    const double d = __shfl_sync(0xffffffffu, gre[k], k);  // the diagonal of a Hermitian matrix is real
+    if (k < M) ok = ok && (d > 0.0) && (d < 1e300);
+    const double dd = (d > 0.0) ? d : 1.0;
+    const double s = rsqrt(dd);
+    const double lkk = dd * s;
+    if (k < M) {
+      dmin = fmin(dmin, lkk);
+      dmax = fmax(dmax, lkk);
+    }
+    const double lr = (lane > k) ? gre[k] * s : (lane == k ? lkk : 0.0);
+    const double li = (lane > k) ? gim[k] * s : 0.0;
+    lre[k] = lr;
+    lim[k] = li;
+    if (lane == k) invd = s;
+#pragma unroll
+    for (int j = k + 1; j < MC; ++j) {
+      // G[lane][j] -= L[lane][k] conj(L[j][k])
+      const double jr = __shfl_sync(0xffffffffu, lr, j), ji = __shfl_sync(0xffffffffu, li, j);
+      gre[j] = fma(-lr, jr, fma(-li, ji, gre[j]));
+      gim[j] = fma(-li, jr, fma(lr, ji, gim[j]));
+    }
+  }
+  return ok && (dmin > 1e-5 * dmax);
+}
+// x[r] = (L^-1)[r][lane] by forward substitution (complex lower triangular L with a real positive diagonal)
+template <int MC>
+DEV void lqc_tri_inverse_cx(const double (&lre)[MC], const double (&lim)[MC], double invd, double (&xre)[MC], double (&xim)[MC],
+                            int lane) {
+#pragma unroll
+  for (int r = 0; r < MC; ++r) {
+    double ar = (r == lane) ? 1.0 : 0.0, ai = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      const double kr = __shfl_sync(0xffffffffu, lre[k], r), ki = __shfl_sync(0xffffffffu, lim[k], r);  // L[r][k] lives in lane r
+      ar = fma(-kr, xre[k], fma(ki, xim[k], ar));
+      ai = fma(-kr, xim[k], fma(-ki, xre[k], ai));
+    }
+    const double dinv = __shfl_sync(0xffffffffu, invd, r);
+    xre[r] = ar * dinv;
+    xim[r] = ai * dinv;
+  }
+}
+
 // =================================================================================================================
 // K1c: one CTA of 4 warps per (item, side)
 // =================================================================================================================
@@ -363,9 +416,17 @@ static inline int lqw_smem_bytes_per_warp(int MB) {
   return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + 4 * MP * (MP + 1) * 8 + 16;
 }
 
-template <int MB>
-__global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_kernel(const EdgeLaunch<double> p, int *flags,
-                                                                                        int smem_per_warp) {
+// CX = true: complex128.  The bond matrix is handled as the REAL matrix of its row-interleaved parts (row 2r = Re P[r],
+// row 2r + 1 = Im P[r]: the (re, im) pairs of the tensor storage, 8 bytes apart): its 2M x 2M real Gram holds the four
+// real products of the complex Gram, and Q1 = W1 P is the real product with the embedding [[Wr, -Wi], [Wi, Wr]] of W1 —
+// exactly the 4 real multiply-adds per complex one, no redundancy, on the same DMMA loops.  Only the two M x M Cholesky /
+// inverse steps and the final L = L1 L2, L^-1 = W2 W1 are done in complex arithmetic.  MB counts 8-row blocks of the real
+// rows (2M <= 8 MB).
+template <int MB, bool CX>
+__global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
+    lq_chol_warp_kernel(const EdgeLaunch<typename std::conditional<CX, cplx, double>::type> p, int *flags, int smem_per_warp) {
+  typedef typename std::conditional<CX, cplx, double>::type S;
+  constexpr int ESZ = CX ? 16 : 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -384,6 +445,7 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
   const SideDesc &sd = ed.s[side];
   const int g = lane >> 2, t = lane & 3;
   const int M = sd.M, N = sd.N, Dk = ed.Dk, ldm = p.ldm;
+  const int MR = CX ? 2 * M : M;  // real rows
 
   unsigned char *mine = smem_raw + (size_t)warp * smem_per_warp;
   LqcCol *cols = (LqcCol *)mine;                      // [LQW_CHUNK]
@@ -415,11 +477,12 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
   }
   __syncwarp();
   const int nenv = sd.nlegs - 1;
-  const char *tbase = (const char *)((const double *)sd.base + (size_t)b * sd.point_stride);
+  const char *tbase = (const char *)sd.base + (size_t)b * sd.point_stride * ESZ;
   auto row_ptr = [&](int r) {
-    const int rr = r < M ? r : 0;
+    const int rq = r < MR ? r : 0;
+    const int rr = CX ? (rq >> 1) : rq, part = CX ? (rq & 1) : 0;
     const int s = rr / Dk, x = rr - s * Dk;
-    return tbase + 8 * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]);
+    return tbase + ESZ * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]) + 8 * part;
   };
   auto build_table = [&](int c0) {
 #pragma unroll
@@ -442,7 +505,7 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
           wv *= wl[k * LQW_WL + x];
         }
         e.ws = wv;
-        e.off = (int)(off * 8u);
+        e.off = (int)(off * (unsigned)ESZ);
       }
       cols[cc] = e;
     }
@@ -524,7 +587,9 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
   store_gram(acc);
   // ------------------------------------------------------------------------------------------------ L1, W1
   bool ok;
-  {
+  constexpr int MC = MP / 2;
+  double *L1c = L1s;  // CX: complex L1 as [MC][MC][2] (re, im); W1s keeps the real embedding of W1 for the DMMA fragments
+  if constexpr (!CX) {
     double gr[MP], l1[MP], invd, x[MP];
 #pragma unroll
     for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
@@ -535,6 +600,30 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
       for (int r = 0; r < MP; ++r) {
         W1s[r * LD + lane] = x[r];
         L1s[lane * LD + r] = l1[r];
+      }
+    }
+  } else {
+    double gre[MC], gim[MC], lre[MC], lim[MC], invd, xre[MC], xim[MC];
+    const int r2 = 2 * (lane < MC ? lane : 0);
+#pragma unroll
+    for (int j = 0; j < MC; ++j) {
+      const bool in = lane < M && j < M;
+      gre[j] = in ? G[r2 * LD + 2 * j] + G[(r2 + 1) * LD + 2 * j + 1] : (lane == j ? 1.0 : 0.0);
+      gim[j] = in ? G[(r2 + 1) * LD + 2 * j] - G[r2 * LD + 2 * j + 1] : 0.0;
+    }
+    ok = lqc_cholesky_cx<MC>(gre, gim, lre, lim, invd, lane, M);
+    lqc_tri_inverse_cx<MC>(lre, lim, invd, xre, xim, lane);
+    __syncwarp();
+    if (lane < MC) {
+#pragma unroll
+      for (int r = 0; r < MC; ++r) {
+        // column `lane` of W1, embedded: rows 2r, 2r+1 x columns 2 lane, 2 lane + 1
+        W1s[(2 * r) * LD + 2 * lane] = xre[r];
+        W1s[(2 * r) * LD + 2 * lane + 1] = -xim[r];
+        W1s[(2 * r + 1) * LD + 2 * lane] = xim[r];
+        W1s[(2 * r + 1) * LD + 2 * lane + 1] = xre[r];
+        L1c[(lane * MC + r) * 2] = lre[r];  // row `lane` of L1
+        L1c[(lane * MC + r) * 2 + 1] = lim[r];
       }
     }
   }
@@ -550,7 +639,7 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const int i = 8 * I + g, k = 4 * ks + t;
-      afr[I][ks] = (i < M && k < M) ? W1s[i * LD + k] : 0.0;
+      afr[I][ks] = (i < MR && k < MR) ? W1s[i * LD + k] : 0.0;
     }
   const char *rowp2[KS];
 #pragma unroll
@@ -603,25 +692,25 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
   }
   store_gram(acc);
   // ------------------------------------------------------------------------------------------------ L2, W2, products
-  {
-    double gr[MP], l2[MP], invd, x[MP];
+  if constexpr (!CX) {
+    {
+      double gr[MP], l2[MP], invd, x[MP];
 #pragma unroll
-    for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
-    ok = lqc_cholesky<MP>(gr, l2, invd, lane, M);
-    lqc_tri_inverse<MP>(l2, invd, x, lane);
-    __syncwarp();
-    if (lane < MP) {
+      for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
+      ok = lqc_cholesky<MP>(gr, l2, invd, lane, M);
+      lqc_tri_inverse<MP>(l2, invd, x, lane);
+      __syncwarp();
+      if (lane < MP) {
 #pragma unroll
-      for (int r = 0; r < MP; ++r) {
-        W2s[r * LD + lane] = x[r];
-        G[lane * LD + r] = l2[r];  // L2 takes the Gram matrix's place
+        for (int r = 0; r < MP; ++r) {
+          W2s[r * LD + lane] = x[r];
+          G[lane * LD + r] = l2[r];  // L2 takes the Gram matrix's place
+        }
       }
     }
-  }
-  __syncwarp();
-  {
+    __syncwarp();
     const double *L2s = G;
-    double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+    double *small = (double *)p.small + (size_t)item * SM_COUNT * ldm * ldm;
     double *gL = small + (SM_L0 + side) * ldm * ldm;
     double *gW = small + (SM_S0 + side) * ldm * ldm;
     for (int idx = lane; idx < M * M; idx += 32) {
@@ -642,15 +731,66 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2) lq_chol_warp_
       gW[r * ldm + j] = c0 + c1;
     }
     if (lane == 0) flags[w] = ok ? 0 : 1;
+  } else {
+    double *L2c = W2s;                    // [MC][MC][2]
+    double *W2c = W2s + MC * MC * 2;      // [MC][MC][2]  (MP * LD >= 4 MC^2)
+    {
+      double gre[MC], gim[MC], lre[MC], lim[MC], invd, xre[MC], xim[MC];
+      const int r2 = 2 * (lane < MC ? lane : 0);
+#pragma unroll
+      for (int j = 0; j < MC; ++j) {
+        const bool in = lane < M && j < M;
+        gre[j] = in ? G[r2 * LD + 2 * j] + G[(r2 + 1) * LD + 2 * j + 1] : (lane == j ? 1.0 : 0.0);
+        gim[j] = in ? G[(r2 + 1) * LD + 2 * j] - G[r2 * LD + 2 * j + 1] : 0.0;
+      }
+      ok = lqc_cholesky_cx<MC>(gre, gim, lre, lim, invd, lane, M);
+      lqc_tri_inverse_cx<MC>(lre, lim, invd, xre, xim, lane);
+      __syncwarp();
+      if (lane < MC) {
+#pragma unroll
+        for (int r = 0; r < MC; ++r) {
+          L2c[(lane * MC + r) * 2] = lre[r];
+          L2c[(lane * MC + r) * 2 + 1] = lim[r];
+          W2c[(r * MC + lane) * 2] = xre[r];  // column `lane` of W2
+          W2c[(r * MC + lane) * 2 + 1] = xim[r];
+        }
+      }
+    }
+    __syncwarp();
+    // L = L1 L2 and L^-1 = W2 W1 in complex arithmetic; W1 is read back from its embedding (re at [2r][2c], im at [2r+1][2c])
+    cplx *small = (cplx *)p.small + (size_t)item * SM_COUNT * ldm * ldm;
+    cplx *gL = small + (SM_L0 + side) * ldm * ldm;
+    cplx *gW = small + (SM_S0 + side) * ldm * ldm;
+    for (int idx = lane; idx < M * M; idx += 32) {
+      const int r = idx / M, j = idx - r * M;
+      double ar = 0.0, ai = 0.0, cr = 0.0, ci = 0.0;
+      for (int k = j; k <= r; ++k) {
+        const double l1r = L1c[(r * MC + k) * 2], l1i = L1c[(r * MC + k) * 2 + 1];
+        const double l2r = L2c[(k * MC + j) * 2], l2i = L2c[(k * MC + j) * 2 + 1];
+        ar = fma(l1r, l2r, fma(-l1i, l2i, ar));
+        ai = fma(l1r, l2i, fma(l1i, l2r, ai));
+        const double w2r = W2c[(r * MC + k) * 2], w2i = W2c[(r * MC + k) * 2 + 1];
+        const double w1r = W1s[(2 * k) * LD + 2 * j], w1i = W1s[(2 * k + 1) * LD + 2 * j];
+        cr = fma(w2r, w1r, fma(-w2i, w1i, cr));
+        ci = fma(w2r, w1i, fma(w2i, w1r, ci));
+      }
+      gL[r * ldm + j] = mkc(ar, ai);
+      gW[r * ldm + j] = mkc(cr, ci);
+    }
+    if (lane == 0) flags[w] = ok ? 0 : 1;
   }
 }
 
 // =================================================================================================================
 // K3c: T'[:, c] = tscale (r~ L^-1) T[:, c], in place, one warp (= one CTA) per (item, side)
 // =================================================================================================================
-template <int MB>
-__global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_THREADS)) recompose_chol_kernel(const EdgeLaunch<double> p,
-                                                                                       const int *flags) {
+// CX = true: complex128 through the same real-embedding as lq_chol_warp_kernel: A = the embedding of r~ L^-1 (2 Mout x 2M),
+// B = the row-interleaved (re, im) tile of the old tensor.
+template <int MB, bool CX>
+__global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_THREADS))
+    recompose_chol_kernel(const EdgeLaunch<typename std::conditional<CX, cplx, double>::type> p, const int *flags) {
+  typedef typename std::conditional<CX, cplx, double>::type S;
+  constexpr int ESZ = CX ? 16 : 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, KS = 2 * MB;
   const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
@@ -663,13 +803,14 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int M = sd.M, N = sd.N, Mout = sd.Mout, Dk = ed.Dk, Dnew = ed.Dnew, ldm = p.ldm;
+  const int MR = CX ? 2 * M : M, MoutR = CX ? 2 * Mout : Mout;  // real rows
 
   int *coff = (int *)smem_raw;                             // [LQC_CHUNK] byte offset of each column (same before / after)
   LqcLeg *legs = (LqcLeg *)(coff + LQC_CHUNK);
-  double *matR = (double *)(legs + TNSU_MAX_LEGS);         // r~ (Mout x M)
-  double *matW = matR + ldm * ldm;                         // L^-1 (M x M)
-  double *matC = matW + ldm * ldm;                         // r~ L^-1
-  double *nred = matC + ldm * ldm;
+  S *matR = (S *)(legs + TNSU_MAX_LEGS);                   // r~ (Mout x M)
+  S *matW = matR + ldm * ldm;                              // L^-1 (M x M)
+  S *matC = matW + ldm * ldm;                              // r~ L^-1
+  double *nred = (double *)(matC + ldm * ldm);
 
   if (tid < TNSU_MAX_LEGS) {
     int l = sd.nlegs - 1 - tid;
@@ -683,22 +824,22 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
       legs[tid] = L;
     }
   }
-  const double *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
-  const double *gR = small + (SM_R0 + side) * ldm * ldm;
-  const double *gW = small + (SM_S0 + side) * ldm * ldm;
+  const S *small = p.small + (size_t)item * SM_COUNT * ldm * ldm;
+  const S *gR = small + (SM_R0 + side) * ldm * ldm;
+  const S *gW = small + (SM_S0 + side) * ldm * ldm;
   for (int idx = tid; idx < Mout * ldm; idx += RCC_THREADS) matR[idx] = gR[idx];
   for (int idx = tid; idx < M * ldm; idx += RCC_THREADS) matW[idx] = gW[idx];
   const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
   __syncthreads();
   for (int idx = tid; idx < Mout * M; idx += RCC_THREADS) {
     const int i = idx / M, j = idx - i * M;
-    double a0 = 0.0, a1 = 0.0;
+    S a0 = from_real<S>(0.0), a1 = from_real<S>(0.0);
     int k = j;
     for (; k + 1 < M; k += 2) {
-      a0 = fma(matR[i * ldm + k], matW[k * ldm + j], a0);
-      a1 = fma(matR[i * ldm + k + 1], matW[(k + 1) * ldm + j], a1);
+      fma_acc(a0, matR[i * ldm + k], matW[k * ldm + j]);
+      fma_acc(a1, matR[i * ldm + k + 1], matW[(k + 1) * ldm + j]);
     }
-    if (k < M) a0 = fma(matR[i * ldm + k], matW[k * ldm + j], a0);
+    if (k < M) fma_acc(a0, matR[i * ldm + k], matW[k * ldm + j]);
     matC[i * ldm + j] = (a0 + a1) * tsc;
   }
   __syncthreads();
@@ -708,22 +849,33 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const int i = 8 * I + g, k = 4 * ks + t;
-      afr[I][ks] = (i < Mout && k < M) ? matC[i * ldm + k] : 0.0;
+      double v = 0.0;
+      if (i < MoutR && k < MR) {
+        if constexpr (CX) {
+          const cplx cv = ((const cplx *)matC)[(i >> 1) * ldm + (k >> 1)];
+          v = ((i & 1) == (k & 1)) ? cv.x : ((i & 1) ? cv.y : -cv.y);  // embedding [[cr, -ci], [ci, cr]]
+        } else {
+          v = ((const double *)matC)[i * ldm + k];
+        }
+      }
+      afr[I][ks] = v;
     }
-  char *tbase = (char *)((double *)sd.base + (size_t)b * sd.point_stride);
+  char *tbase = (char *)sd.base + (size_t)b * sd.point_stride * ESZ;
   const char *rowin[KS];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
-    const int r = 4 * ks + t < M ? 4 * ks + t : 0;
+    const int rq = 4 * ks + t < MR ? 4 * ks + t : 0;
+    const int r = CX ? (rq >> 1) : rq, part = CX ? (rq & 1) : 0;
     const int s = r / Dk, x = r - s * Dk;
-    rowin[ks] = tbase + 8 * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]);
+    rowin[ks] = tbase + ESZ * ((long long)s * sd.in_stride_phys + (long long)x * sd.in_stride[sd.bond_leg]) + 8 * part;
   }
   long long rowout[MB];
 #pragma unroll
   for (int I = 0; I < MB; ++I) {
-    const int r = 8 * I + g < Mout ? 8 * I + g : 0;
+    const int rq = 8 * I + g < MoutR ? 8 * I + g : 0;
+    const int r = CX ? (rq >> 1) : rq, part = CX ? (rq & 1) : 0;
     const int s = r / Dnew, x = r - s * Dnew;
-    rowout[I] = 8 * ((long long)s * sd.out_stride_phys + (long long)x * sd.out_stride[sd.bond_leg]);
+    rowout[I] = ESZ * ((long long)s * sd.out_stride_phys + (long long)x * sd.out_stride[sd.bond_leg]) + 8 * part;
   }
   const int nenv = sd.nlegs - 1;
   // 32-byte accesses are possible when the innermost tensor axis is an environment leg whose dimension is a multiple of 4
@@ -732,7 +884,7 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
   bool vec_cols = false;
   {
     const int lin = sd.nlegs - 1;
-    if (sd.bond_leg != lin && lin >= 0 && sd.dims[lin] % 4 == 0 && sd.in_stride[lin] == 1 && sd.in_stride[sd.bond_leg] % 4 == 0 &&
+    if (!CX && sd.bond_leg != lin && lin >= 0 && sd.dims[lin] % 4 == 0 && sd.in_stride[lin] == 1 && sd.in_stride[sd.bond_leg] % 4 == 0 &&
         sd.in_stride_phys % 4 == 0 && sd.point_stride % 4 == 0 && (((size_t)sd.base & 31) == 0))
       vec_cols = true;
   }
@@ -750,7 +902,7 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
           rem = qq;
         }
       }
-      coff[cc] = (int)(off * 8u);
+      coff[cc] = (int)(off * (unsigned)ESZ);
     }
     __syncthreads();
     const int ncols = min(LQC_CHUNK, N - c0);
@@ -782,7 +934,7 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) lqc_dmma(da[j], db[j], afr[I][ks], bv[ks][j]);
           }
-          if (8 * I + g < Mout) {
+          if (8 * I + g < MoutR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) n2 = fma(da[j], da[j], fma(db[j], db[j], n2));
             asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(tbase + rowout[I] + oa), "d"(da[0]), "d"(da[1]),
@@ -815,7 +967,7 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
       __syncwarp();  // every lane of the warp has its inputs: the stores below overwrite the same tile
 #pragma unroll
       for (int I = 0; I < MB; ++I) {
-        if (8 * I + g < Mout) {
+        if (8 * I + g < MoutR) {
           if (ca < ncols) {
             n2 = fma(d0[I], d0[I], n2);
             *(double *)(tbase + rowout[I] + o0) = d0[I];
@@ -839,14 +991,14 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
   }
 }
 
-static inline int rcc_smem_bytes(int ldm) { return LQC_CHUNK * 4 + TNSU_MAX_LEGS * 16 + 3 * ldm * ldm * 8 + 64; }
+static inline int rcc_smem_bytes(int ldm, int esz = 8) { return LQC_CHUNK * 4 + TNSU_MAX_LEGS * 16 + 3 * ldm * ldm * esz + 64; }
 
 template <int MB>
 cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flags, cudaStream_t st) {
   auto kern = lq_chol_kernel<MB>;
   if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   if (p.lqc_force_fallback != 2) {  // default: one warp per (item, side); 2 selects the two-warp-CTA kernel (A/B comparisons)
-    auto kw = lq_chol_warp_kernel<MB>;
+    auto kw = lq_chol_warp_kernel<MB, false>;
     if (cudaError_t s = tnsu_opt_in_smem((const void *)kw); s != cudaSuccess) return s;
     const int per_warp = lqw_smem_bytes_per_warp(MB);
     kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
@@ -857,10 +1009,40 @@ cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flag
 }
 template <int MB>
 cudaError_t launch_rc_chol_v(const EdgeLaunch<double> &p, int n_items, const int *flags, cudaStream_t st) {
-  auto kern = recompose_chol_kernel<MB>;
+  auto kern = recompose_chol_kernel<MB, false>;
   if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
   kern<<<2 * n_items, RCC_THREADS, rcc_smem_bytes(p.ldm), st>>>(p, flags);
   return cudaGetLastError();
+}
+// complex128: m_max complex rows -> 2 m_max real rows
+template <int MB>
+cudaError_t launch_lq_chol_cx_v(const EdgeLaunch<cplx> &p, int n_items, int *flags, cudaStream_t st) {
+  auto kw = lq_chol_warp_kernel<MB, true>;
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kw); s != cudaSuccess) return s;
+  const int per_warp = lqw_smem_bytes_per_warp(MB);
+  kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
+  return cudaGetLastError();
+}
+template <int MB>
+cudaError_t launch_rc_chol_cx_v(const EdgeLaunch<cplx> &p, int n_items, const int *flags, cudaStream_t st) {
+  auto kern = recompose_chol_kernel<MB, true>;
+  if (cudaError_t s = tnsu_opt_in_smem((const void *)kern); s != cudaSuccess) return s;
+  kern<<<2 * n_items, RCC_THREADS, rcc_smem_bytes(p.ldm, 16), st>>>(p, flags);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_lq_chol_cx(const EdgeLaunch<cplx> &p, int n_items, int m_max, int *flags, cudaStream_t st) {
+  const int mb = (2 * m_max + 7) / 8;
+  if (mb <= 1) return launch_lq_chol_cx_v<1>(p, n_items, flags, st);
+  if (mb == 2) return launch_lq_chol_cx_v<2>(p, n_items, flags, st);
+  if (mb == 3) return launch_lq_chol_cx_v<3>(p, n_items, flags, st);
+  return launch_lq_chol_cx_v<4>(p, n_items, flags, st);
+}
+inline cudaError_t launch_rc_chol_cx(const EdgeLaunch<cplx> &p, int n_items, int m_max, const int *flags, cudaStream_t st) {
+  const int mb = (2 * m_max + 7) / 8;
+  if (mb <= 1) return launch_rc_chol_cx_v<1>(p, n_items, flags, st);
+  if (mb == 2) return launch_rc_chol_cx_v<2>(p, n_items, flags, st);
+  if (mb == 3) return launch_rc_chol_cx_v<3>(p, n_items, flags, st);
+  return launch_rc_chol_cx_v<4>(p, n_items, flags, st);
 }
 inline cudaError_t launch_lq_chol(const EdgeLaunch<double> &p, int n_items, int m_max, int *flags, cudaStream_t st) {
   const int mb = (m_max + 7) / 8;

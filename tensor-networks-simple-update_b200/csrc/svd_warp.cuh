@@ -83,7 +83,7 @@ DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (
 //   flip = false:  x' = s x + c y,  y' = c x - s y        flip = true:  x' = -s x + c y,  y' = c x + s y
 // where (c, s) come from (al, be, ga) = (|P|^2, |Q|^2, P.Q) of the ordered pair (P, Q) = flip ? (y, x) : (x, y).
 template <int R>
-DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
+DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
   double nx0 = 0.0, nx1 = 0.0, ny0 = 0.0, ny1 = 0.0, ga0 = 0.0, ga1 = 0.0;
 #pragma unroll
   for (int r = 0; r < R; r += 2) {
@@ -103,7 +103,8 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
   const double al = flip ? ny : nx, be = flip ? nx : ny;
   const double tol2 = 2.25e-30;
   const double g2 = ga * ga;
-  const bool rot = !idle && (g2 > tol2 * al * be) && (g2 > 0.0);
+  const double ab = al * be;
+  const bool rot = !idle && (g2 > tol2 * ab) && (g2 > 0.0);
   double c = 1.0, s = 0.0;
   if (rot) {
     const double delta = be - al;
@@ -113,6 +114,8 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
     c = c2 * inv_c;
     s = (delta < 0.0 ? -ga : ga) * inv_r * inv_c;
   }
+  // a "small" rotation: cosine of the pair <= 1e-10 and |sin| of the rotation <= 1e-7 (see the sweep loop)
+  const unsigned kind = rot ? (((g2 <= 1e-20 * ab) && (s * s <= 1e-14)) ? 1u : 3u) : 0u;
   if (idle) {
     c = 0.0;
     s = 1.0;
@@ -124,7 +127,7 @@ DEV bool svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
     xa[r] = fma(sa, x0, c * y0);
     ya[r] = fma(c, x0, -(sa * y0));
   }
-  return rot;
+  return kind;
 }
 
 // Everything one call of the warp SVD needs.  The edge-update kernel K2 (svd_warp_kernel) fills it per (point, edge)
@@ -479,17 +482,24 @@ DEV void svdw_body(const SvdwArgs &args) {
   } else {
     // one half step per trip (step A: pair (x_k, y_k), then x_k <- x_{k+1}; step B: pair (y_k, x_k), the last
     // processor idle, then x_k <- x_{k-1}): a single copy of the step in the instruction stream
+    // The iteration ends after a sweep without rotation — or after a sweep whose rotations were all SMALL: every pair
+    // met had a cosine <= 1e-10 and was rotated by |sin| <= 1e-7.  A pair made orthogonal in such a sweep is disturbed
+    // afterwards only by the later rotations of its two columns, each adding at most |sin| x (cosine of the third
+    // column) <= 1e-17, at most 2 (n - 1) times: <= 6.2e-16 at n = 32, below the 1.5e-15 a further sweep would test
+    // for.  That sweep would rotate nothing; skipping it saves one of the ~7 sweeps of a 32 x 32 theta.  Pairs of
+    // (nearly) equal singular values rotate by large angles at tiny cosines: they are not small, and the usual
+    // rotation-free sweep confirms them.
     for (; sweeps < max_sweeps; ++sweeps) {
-      bool rotated = false;
+      unsigned kinds = 0u;
 #pragma unroll 1
       for (int st = 0; st < 2 * NP; ++st) {
         const bool flip = (st & 1) != 0;
-        rotated |= svdw_step_a<R>(xa, ya, flip, flip && last);
+        kinds |= svdw_step_a<R>(xa, ya, flip, flip && last);
         const int src = flip ? src_prev : src_next;
 #pragma unroll
         for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src);
       }
-      if (!__any_sync(0xffffffffu, rotated)) {
+      if (!__any_sync(0xffffffffu, (kinds & 2u) != 0u)) {
         ++sweeps;
         jacobi_done = true;
         break;
