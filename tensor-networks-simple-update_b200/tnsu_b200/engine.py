@@ -81,18 +81,29 @@ class Engine:
         a = np.ascontiguousarray(values, dtype=self.dtype).reshape(self.batch, -1)
         self._check(self._lib.tnsu_set_tensor(self._h, t, _ptr(a), a.shape[1]))
 
-    def get_tensor(self, t: int) -> np.ndarray:
+    def get_tensor(self, t: int, out: np.ndarray | None = None) -> np.ndarray:
+        """Tensor t of every point, [batch, d, D_1..D_z].  `out`: a C-contiguous array of that shape and the engine dtype
+        to download into (page-locked memory makes the copy run at PCIe speed; a fresh numpy array is pageable)."""
         shape = self.tensor_shape(t)
-        out = np.empty((self.batch, int(np.prod(shape))), dtype=self.dtype)
-        self._check(self._lib.tnsu_get_tensor(self._h, t, _ptr(out), out.shape[1]))
+        n = int(np.prod(shape))
+        if out is None:
+            out = np.empty((self.batch, n), dtype=self.dtype)
+        elif out.dtype != self.dtype or out.size != self.batch * n or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous {np.dtype(self.dtype).name} array of {self.batch * n} elements")
+        self._check(self._lib.tnsu_get_tensor(self._h, t, _ptr(out), n))
         return out.reshape((self.batch,) + shape)
 
     def set_weights(self, e: int, values: np.ndarray):
         a = np.ascontiguousarray(values, dtype=np.float64).reshape(self.batch, -1)
         self._check(self._lib.tnsu_set_weights(self._h, e, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[1]))
 
-    def get_weights(self, e: int) -> np.ndarray:
-        out = np.empty((self.batch, int(self.edge_dims[e])), dtype=np.float64)
+    def get_weights(self, e: int, out: np.ndarray | None = None) -> np.ndarray:
+        n = int(self.edge_dims[e])
+        if out is None:
+            out = np.empty((self.batch, n), dtype=np.float64)
+        elif out.dtype != np.float64 or out.size != self.batch * n or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float64 array of {self.batch * n} elements")
+        out = out.reshape(self.batch, n)
         self._check(self._lib.tnsu_get_weights(self._h, e, out.ctypes.data_as(C.POINTER(C.c_double)), out.shape[1]))
         return out
 

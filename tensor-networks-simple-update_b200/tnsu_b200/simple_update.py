@@ -172,20 +172,20 @@ class SimpleUpdateBatch:
         which applies the same Pade routine per matrix (bit-identical to the reference's one-matrix calls, :470-473;
         checked in tests/test_host.py)."""
         n_p, m = hams.shape[:2]
-        index, uniq_h, uniq_dt = {}, [], []
-        which = np.empty((n_p, m), dtype=np.int64)
-        for p in range(n_p):
-            dt = complex(dts_of_point[p])
-            for ek in range(m):
-                key = (hams[p, ek].tobytes(), dt)
-                k = index.get(key)
-                if k is None:
-                    k = index[key] = len(uniq_h)
-                    uniq_h.append(hams[p, ek])
-                    uniq_dt.append(dts_of_point[p])
-                which[p, ek] = k
-        stack = np.array([-dt * h for dt, h in zip(uniq_dt, uniq_h)])
-        return linalg.expm(stack)[which]
+        d2 = hams.shape[-1]
+        dts = np.array([complex(x) for x in dts_of_point])
+        if np.all(dts.imag == 0.0):
+            dts = dts.real
+        # distinct (H, dt) pairs: one row of bytes per (point, edge) = the Hamiltonian followed by its time step
+        rows = np.empty((n_p * m, d2 * d2 + 1), dtype=np.complex128)
+        rows[:, :-1] = hams.reshape(n_p * m, d2 * d2)
+        rows[:, -1] = np.repeat(dts, m)
+        _, first, which = np.unique(rows.view(np.dtype((np.void, rows.shape[1] * 16))).ravel(), return_index=True,
+                                    return_inverse=True)
+        uniq_h = hams.reshape(n_p * m, d2, d2)[first]
+        uniq_dt = np.repeat(dts, m)[first]
+        stack = -uniq_dt[:, None, None] * uniq_h
+        return linalg.expm(stack)[which.reshape(n_p, m)]
 
     # ------------------------------------------------------------------ engine lifecycle
     def _current_dims(self):
