@@ -84,6 +84,7 @@ struct EdgeLaunch {
   int svdw_accv;             // 1: accumulate the right rotations in registers; 0: V-free iteration, vectors recovered from theta
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;
+  int svd_vfree;             // shared-memory SVD kernel: iterate A alone, recover the kept right vectors from the initial A afterwards
   int svd_max_sweeps;        // Jacobi sweep limit (60 for the warp kernel, 40 for the shared-memory one; TNSU_SVD_MAX_SWEEPS overrides: tests)
   int *status;               // [2] device failure counters: [0] != 0 once a theta had no finite positive singular-value sum
                              // (NaN / Inf in the state), [1] Jacobi iterations that hit their sweep limit
@@ -838,11 +839,14 @@ DEV void jacobi_rotation(double al, double be, cplx ga, double &c, cplx &sp, cpl
 
 // A is nr x nc column-major (nr >= nc), V nc x nc.  RPL = rows of A per lane, CPL = rows of V per lane.
 template <typename S, int RPL, int CPL>
-__device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile int *flag, int tid, int nthr, int max_sweeps) {
-  for (int idx = tid; idx < nc * nc; idx += nthr) {
-    int col = idx / nc, row = idx - col * nc;
-    V[col * ldv + row] = from_real<S>(row == col ? 1.0 : 0.0);
-  }
+__device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile int *flag, int tid, int nthr, int max_sweeps,
+                          bool accv) {
+  // accv = false: the right rotations are not accumulated (V is not touched): the caller recovers the vectors it needs
+  if (accv)
+    for (int idx = tid; idx < nc * nc; idx += nthr) {
+      int col = idx / nc, row = idx - col * nc;
+      V[col * ldv + row] = from_real<S>(row == col ? 1.0 : 0.0);
+    }
   const int lane8 = tid & (SVD_LPP - 1);
   const int group = tid / SVD_LPP;
   const int ngroups = nthr / SVD_LPP;
@@ -886,8 +890,8 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
 #pragma unroll
           for (int u = 0; u < CPL; ++u) {
             const int i = lane8 + u * SVD_LPP;
-            vx[u] = (i < nc) ? vp[i] : from_real<S>(0.0);
-            vy[u] = (i < nc) ? vq[i] : from_real<S>(0.0);
+            vx[u] = (accv && i < nc) ? vp[i] : from_real<S>(0.0);
+            vy[u] = (accv && i < nc) ? vq[i] : from_real<S>(0.0);
           }
           double al = 0.0, be = 0.0;
           S ga = from_real<S>(0.0);
@@ -916,12 +920,14 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
                 aq[i] = sq * x[u] + y[u] * c;
               }
             }
+            if (accv) {
 #pragma unroll
-            for (int u = 0; u < CPL; ++u) {
-              const int i = lane8 + u * SVD_LPP;
-              if (i < nc) {
-                vp[i] = vx[u] * c - sp * vy[u];
-                vq[i] = sq * vx[u] + vy[u] * c;
+              for (int u = 0; u < CPL; ++u) {
+                const int i = lane8 + u * SVD_LPP;
+                if (i < nc) {
+                  vp[i] = vx[u] * c - sp * vy[u];
+                  vq[i] = sq * vx[u] + vy[u] * c;
+                }
               }
             }
             if (lane8 == 0) *flag = 1;
@@ -973,9 +979,17 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
   S *svdA = gate_s + p.d4;
   // V (nc x nc) overlays L_i | L_j, which are dead once theta is built, whenever it fits there (a third less shared
   // memory per theta: 4 instead of 3 resident CTAs per SM at 32 x 32 complex128)
-  const bool v_on_l = (size_t)p.ldv * p.ldv <= (size_t)2 * ldm * ldm;
+  // V-free iteration (p.svd_vfree): a copy A0 of the initial A sits where V would, nothing is accumulated, and the Dnew
+  // right vectors that survive the truncation are recovered at the end as w_x = A0^H u_x / ||A0^H u_x|| (+ two passes of
+  // modified Gram-Schmidt) into Wk [dcap][ldv].  The accumulator is 2/7 of the iteration's shared-memory traffic and
+  // flops, and this kernel runs at 73 % of the shared-memory bandwidth (profiles/r02).
+  const bool vfree = p.svd_vfree != 0;
+  const bool v_on_l = !vfree && (size_t)p.ldv * p.ldv <= (size_t)2 * ldm * ldm;
   S *svdV = v_on_l ? Li : svdA + (size_t)p.lda * p.ldv;  // nc <= ldv columns
-  double *sig = (double *)(svdA + (size_t)p.lda * p.ldv + (v_on_l ? 0 : (size_t)p.ldv * p.ldv));
+  S *A0 = svdA + (size_t)p.lda * p.ldv;                  // V-free: [nc][lda] like A
+  S *Wk = A0 + (size_t)p.lda * p.ldv;                    // V-free: [Dnew][ldv]
+  double *sig = (double *)(svdA + (size_t)p.lda * p.ldv +
+                           (vfree ? (size_t)p.lda * p.ldv + (size_t)p.dcap * p.ldv : (v_on_l ? 0 : (size_t)p.ldv * p.ldv)));
   double *lam_old = sig + TNSU_MAX_SVD;
   int *order = (int *)(lam_old + TNSU_MAX_SVD);
   int *flag = order + TNSU_MAX_SVD;
@@ -1026,8 +1040,11 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
       }
   }
   long long clk1 = clock64();
-  __syncthreads();  // every read of L_i / L_j is done before V is initialised on top of them
-  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40));
+  __syncthreads();  // theta is complete; every read of L_i / L_j is done before V is written on top of them
+  if (vfree) {
+    for (int idx = tid; idx < nc * p.lda; idx += nthr) A0[idx] = svdA[idx];
+  }
+  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40), !vfree);
   long long clk2 = clock64();
 
   // singular values, descending order
@@ -1061,6 +1078,59 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     }
     p.edge_err[(size_t)b * p.m_edges + ek] = (Dnew == Dk) ? sqrt(err2) : nan("");
   }
+  if (vfree) {
+    // w_x[c] = sum_r conj(A0[r][c]) u_x[r],  u_x = (column order[x] of the final A) / sigma_x
+    for (int idx = tid; idx < Dnew * nc; idx += nthr) {
+      const int xp = idx / nc, c = idx - xp * nc;
+      const int oc = order[xp];
+      const S *a0 = A0 + (size_t)c * p.lda, *ax = svdA + (size_t)oc * p.lda;
+      S acc0 = from_real<S>(0.0), acc1 = from_real<S>(0.0);
+      int r = 0;
+      for (; r + 1 < nr; r += 2) {
+        fma_acc(acc0, cj(a0[r]), ax[r]);
+        fma_acc(acc1, cj(a0[r + 1]), ax[r + 1]);
+      }
+      if (r < nr) fma_acc(acc0, cj(a0[r]), ax[r]);
+      const double sv = sig[oc];
+      Wk[(size_t)xp * p.ldv + c] = (acc0 + acc1) * (sv > 0.0 ? 1.0 / sv : 0.0);
+    }
+    __syncthreads();
+    // two passes of modified Gram-Schmidt in rank order; warp w projects the vectors j + 1 + w, j + 1 + w + nwarps, ...
+    const int lane = tid & 31, wid = tid >> 5, nwarps = nthr >> 5;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < Dnew; ++j) {
+        S *wj = Wk + (size_t)j * p.ldv;
+        if (wid == 0) {
+          double n2 = 0.0;
+          for (int c = lane; c < nc; c += 32) n2 += abs2(wj[c]);
+#pragma unroll
+          for (int mm = 16; mm >= 1; mm >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, mm);
+          if (!(n2 > 1e-280)) {
+            // no direction of its own (sigma = 0, or A0^H u underflows): a fixed dense start vector, as in svd_warp.cuh
+            for (int c = lane; c < nc; c += 32)
+              wj[c] = from_real<S>((double)(((unsigned)(c + 1) * 2654435761u ^ (unsigned)(j + 1) * 40503u) >> 8 & 0xffffu) - 32767.5);
+            __syncwarp();
+            n2 = 0.0;
+            for (int c = lane; c < nc; c += 32) n2 += abs2(wj[c]);
+#pragma unroll
+            for (int mm = 16; mm >= 1; mm >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, mm);
+          }
+          const double sc = rsqrt(n2);
+          for (int c = lane; c < nc; c += 32) wj[c] = wj[c] * sc;
+        }
+        __syncthreads();
+        for (int i = j + 1 + wid; i < Dnew; i += nwarps) {
+          S *wi = Wk + (size_t)i * p.ldv;
+          S dot = from_real<S>(0.0);
+          for (int c = lane; c < nc; c += 32) fma_acc(dot, cj(wj[c]), wi[c]);
+#pragma unroll
+          for (int mm = 16; mm >= 1; mm >>= 1) dot = dot + shfl_xor(dot, mm);
+          for (int c = lane; c < nc; c += 32) fms_acc(wi[c], dot, wj[c]);
+        }
+        __syncthreads();
+      }
+    }
+  }
   // r~_i[(i',x'),qi] = U[(qi,i'),x'],   r~_j[(j',x'),qj] = V^H[x',(j',qj)]
   S *rt_i = small + SM_R0 * ldm * ldm, *rt_j = small + SM_R1 * ldm * ldm;
   for (int idx = tid; idx < d * Dnew * Ki; idx += nthr) {
@@ -1070,7 +1140,8 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     const double sv = sig[oc];
     const double isv = sv > 0.0 ? 1.0 / sv : 0.0;
     const int trow = qi * d + ip;
-    rt_i[row * ldm + qi] = transposed ? svdV[(size_t)oc * p.ldv + trow] : svdA[(size_t)oc * p.lda + trow] * isv;
+    const S vval = vfree ? Wk[(size_t)xp * p.ldv + trow] : svdV[(size_t)oc * p.ldv + trow];
+    rt_i[row * ldm + qi] = transposed ? vval : svdA[(size_t)oc * p.lda + trow] * isv;
   }
   for (int idx = tid; idx < d * Dnew * Kj; idx += nthr) {
     const int row = idx / Kj, qj = idx - row * Kj;
@@ -1079,7 +1150,8 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     const double sv = sig[oc];
     const double isv = sv > 0.0 ? 1.0 / sv : 0.0;
     const int tcol = jp * Kj + qj;
-    rt_j[row * ldm + qj] = transposed ? cj(svdA[(size_t)oc * p.lda + tcol] * isv) : cj(svdV[(size_t)oc * p.ldv + tcol]);
+    const S vval = vfree ? Wk[(size_t)xp * p.ldv + tcol] : svdV[(size_t)oc * p.ldv + tcol];
+    rt_j[row * ldm + qj] = transposed ? cj(svdA[(size_t)oc * p.lda + tcol] * isv) : cj(vval);
   }
   if (p.dbg_info != nullptr && b == p.dbg_point) {
     for (int j = tid; j < nc; j += nthr) p.dbg_sigma[j] = sig[order[j]];

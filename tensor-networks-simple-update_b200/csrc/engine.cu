@@ -34,6 +34,7 @@ struct LevelCfg {
   int lq_stream_grid = 0, lq_stage_off = 0, lq_stage_doubles = 0;  // persistent TMA-staged K1
   int cluster = 1;                                                   // CTAs per (item, side) in K1 / K3
   int svdw_np = 0, svdw_rows = 0, svdw_group_doubles = 0;  // register-resident warp SVD (0 = shared-memory kernel)
+  int svd_vfree = 0;                                         // shared-memory SVD kernel without the accumulator (edge_update.cuh)
 };
 
 struct tnsu_engine {
@@ -332,8 +333,15 @@ static int plan_sweep(tnsu_engine *e) {
         c.lq_stream_grid = 2 * e->num_sms;
       }
     }
-    c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv)) * ssz + 2 * TNSU_MAX_SVD * 8 +
-                 TNSU_MAX_SVD * 4 + 64;
+    c.svd_vfree = e->svd_accumulate_v ? 0 : 1;
+    c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv +
+                  (c.svd_vfree ? c.lda * c.ldv + e->dcap * c.ldv : (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv))) * ssz +
+                 2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
+    if (c.svd_vfree && c.smem_svd > SMEM_LIMIT) {  // the accumulating variant needs less shared memory for very large thetas
+      c.svd_vfree = 0;
+      c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv + (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv)) * ssz +
+                   2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
+    }
     c.smem_rc = TNSU_MAX_LEGS * e->dcap * 8 + c.mm_t * 8 + 3 * ldm2 * ssz + TNSU_MAX_WARPS * 8 + 64;
     // real thetas of at most 32 x 32 take the register-resident warp kernel (svd_warp.cuh)
     if (!cx && maxnr <= 32 && !e->force_smem_svd) {
@@ -555,6 +563,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.lq_stats = nullptr;
     p.lqc_force_fallback = e->lqc_force_fallback ? 1 : (e->lqc_cta_kernel ? 2 : 0);
     p.svdw_accv = c.svdw_accv;
+    p.svd_vfree = c.svd_vfree;
     p.svdw_tb_off = c.svdw_tb_off;
     p.status = e->d_status;
     p.svd_max_sweeps = e->svd_max_sweeps;
