@@ -675,7 +675,7 @@ def main():
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--energy-steps", type=int, default=10)
-    ap.add_argument("--e2e-chunks", type=int, default=2)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     args = ap.parse_args()
