@@ -152,6 +152,107 @@ DEV void lqc_tri_inverse_cx(const double (&lre)[MC], const double (&lim)[MC], do
   }
 }
 
+// ---- the same two steps for the one-warp-per-matrix kernel with the lane-to-lane broadcasts through shared memory instead
+// of shuffles: an FP64 shuffle is ~6 SASS instructions, the O(MP^2) of them made these helpers 10 k of the kernel's 15.8 k
+// instructions (27 k for complex128) against a 32 KB instruction cache — ncu (profiles/r02) showed 0.7 (complex: 3.2)
+// issue slots lost to instruction fetch per slot used.  `scr` = 64 doubles of per-warp scratch (128 for complex). ----
+template <int MP>
+DEV bool lqc_cholesky_s(double (&g)[MP], double (&l)[MP], double &invd, int lane, int M, double *scr) {
+  bool ok = true;
+  double dmin = 1e300, dmax = 0.0;
+  invd = 1.0;
+#pragma unroll
+  for (int k = 0; k < MP; ++k) {
+    double *col = scr + (k & 1) * 32;
+    const double d = __shfl_sync(0xffffffffu, g[k], k);
+    if (k < M) ok = ok && (d > 0.0) && (d < 1e300);
+    const double dd = (d > 0.0) ? d : 1.0;
+    const double s = rsqrt(dd);
+    const double lkk = dd * s;
+    if (k < M) {
+      dmin = fmin(dmin, lkk);
+      dmax = fmax(dmax, lkk);
+    }
+    const double lk = (lane >= k) ? g[k] * s : 0.0;
+    l[k] = lk;
+    if (lane == k) invd = s;
+    col[lane] = lk;
+    __syncwarp();
+#pragma unroll
+    for (int j = k + 1; j < MP; ++j) g[j] = fma(-lk, col[j], g[j]);
+  }
+  return ok && (dmin > 1e-5 * dmax);
+}
+// Ls: L row-major with leading dimension LD, dinv[r] = 1 / L[r][r], both in shared memory and complete
+template <int MP>
+DEV void lqc_tri_inverse_s(const double *Ls, int LD, const double *dinv, double (&x)[MP], int lane) {
+#pragma unroll
+  for (int r = 0; r < MP; ++r) {
+    double a0 = (r == lane) ? 1.0 : 0.0, a1 = 0.0;
+    const double *lr = Ls + r * LD;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      if (k & 1)
+        a1 = fma(-lr[k], x[k], a1);
+      else
+        a0 = fma(-lr[k], x[k], a0);
+    }
+    x[r] = (a0 + a1) * dinv[r];
+  }
+}
+template <int MC>
+DEV bool lqc_cholesky_cx_s(double (&gre)[MC], double (&gim)[MC], double (&lre)[MC], double (&lim)[MC], double &invd, int lane, int M,
+                           double *scr) {
+  bool ok = true;
+  double dmin = 1e300, dmax = 0.0;
+  invd = 1.0;
+#pragma unroll
+  for (int k = 0; k < MC; ++k) {
+    double *col = scr + (k & 1) * 64;
+    const double d = __shfl_sync(0xffffffffu, gre[k], k);
+    if (k < M) ok = ok && (d > 0.0) && (d < 1e300);
+    const double dd = (d > 0.0) ? d : 1.0;
+    const double s = rsqrt(dd);
+    const double lkk = dd * s;
+    if (k < M) {
+      dmin = fmin(dmin, lkk);
+      dmax = fmax(dmax, lkk);
+    }
+    const double lr = (lane > k) ? gre[k] * s : (lane == k ? lkk : 0.0);
+    const double li = (lane > k) ? gim[k] * s : 0.0;
+    lre[k] = lr;
+    lim[k] = li;
+    if (lane == k) invd = s;
+    col[2 * lane] = lr;
+    col[2 * lane + 1] = li;
+    __syncwarp();
+#pragma unroll
+    for (int j = k + 1; j < MC; ++j) {
+      const double jr = col[2 * j], ji = col[2 * j + 1];  // G[lane][j] -= L[lane][k] conj(L[j][k])
+      gre[j] = fma(-lr, jr, fma(-li, ji, gre[j]));
+      gim[j] = fma(-li, jr, fma(lr, ji, gim[j]));
+    }
+  }
+  return ok && (dmin > 1e-5 * dmax);
+}
+// Lc: complex L as [MC][MC][2] (re, im) in shared memory, dinv[r] = 1 / L[r][r]
+template <int MC>
+DEV void lqc_tri_inverse_cx_s(const double *Lc, const double *dinv, double (&xre)[MC], double (&xim)[MC], int lane) {
+#pragma unroll
+  for (int r = 0; r < MC; ++r) {
+    double ar = (r == lane) ? 1.0 : 0.0, ai = 0.0;
+    const double *lr = Lc + (size_t)r * MC * 2;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      const double kr = lr[2 * k], ki = lr[2 * k + 1];
+      ar = fma(-kr, xre[k], fma(ki, xim[k], ar));
+      ai = fma(-kr, xim[k], fma(-ki, xre[k], ai));
+    }
+    xre[r] = ar * dinv[r];
+    xim[r] = ai * dinv[r];
+  }
+}
+
 // =================================================================================================================
 // K1c: one CTA of 4 warps per (item, side)
 // =================================================================================================================
@@ -413,7 +514,7 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
 
 static inline int lqw_smem_bytes_per_warp(int MB) {
   const int MP = 8 * MB;
-  return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + 4 * MP * (MP + 1) * 8 + 16;
+  return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + 4 * MP * (MP + 1) * 8 + 160 * 8 + 16;
 }
 
 // CX = true: complex128.  The bond matrix is handled as the REAL matrix of its row-interleaved parts (row 2r = Re P[r],
@@ -453,6 +554,8 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
   double *wl = (double *)(legs + TNSU_MAX_LEGS);      // [legs][LQW_WL]
   double *G = wl + TNSU_MAX_LEGS * LQW_WL;            // Gram matrix of the current pass, later L2
   double *L1s = G + MP * LD, *W1s = L1s + MP * LD, *W2s = W1s + MP * LD;
+  double *scr = W2s + MP * LD;   // [128] column broadcast of the Cholesky steps
+  double *dinv = scr + 128;      // [32] reciprocal diagonal of the current Cholesky factor
 
   const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
   const double tsc = p.tscale[(size_t)b * p.n_tensors + sd.tensor];
@@ -593,14 +696,17 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
     double gr[MP], l1[MP], invd, x[MP];
 #pragma unroll
     for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
-    ok = lqc_cholesky<MP>(gr, l1, invd, lane, M);
-    lqc_tri_inverse<MP>(l1, invd, x, lane);
+    ok = lqc_cholesky_s<MP>(gr, l1, invd, lane, M, scr);
     if (lane < MP) {
 #pragma unroll
-      for (int r = 0; r < MP; ++r) {
-        W1s[r * LD + lane] = x[r];
-        L1s[lane * LD + r] = l1[r];
-      }
+      for (int r = 0; r < MP; ++r) L1s[lane * LD + r] = l1[r];
+      dinv[lane] = invd;
+    }
+    __syncwarp();
+    lqc_tri_inverse_s<MP>(L1s, LD, dinv, x, lane);
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) W1s[r * LD + lane] = x[r];
     }
   } else {
     double gre[MC], gim[MC], lre[MC], lim[MC], invd, xre[MC], xim[MC];
@@ -611,9 +717,17 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
       gre[j] = in ? G[r2 * LD + 2 * j] + G[(r2 + 1) * LD + 2 * j + 1] : (lane == j ? 1.0 : 0.0);
       gim[j] = in ? G[(r2 + 1) * LD + 2 * j] - G[r2 * LD + 2 * j + 1] : 0.0;
     }
-    ok = lqc_cholesky_cx<MC>(gre, gim, lre, lim, invd, lane, M);
-    lqc_tri_inverse_cx<MC>(lre, lim, invd, xre, xim, lane);
+    ok = lqc_cholesky_cx_s<MC>(gre, gim, lre, lim, invd, lane, M, scr);
+    if (lane < MC) {
+#pragma unroll
+      for (int r = 0; r < MC; ++r) {
+        L1c[(lane * MC + r) * 2] = lre[r];  // row `lane` of L1
+        L1c[(lane * MC + r) * 2 + 1] = lim[r];
+      }
+      dinv[lane] = invd;
+    }
     __syncwarp();
+    lqc_tri_inverse_cx_s<MC>(L1c, dinv, xre, xim, lane);
     if (lane < MC) {
 #pragma unroll
       for (int r = 0; r < MC; ++r) {
@@ -622,8 +736,6 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
         W1s[(2 * r) * LD + 2 * lane + 1] = -xim[r];
         W1s[(2 * r + 1) * LD + 2 * lane] = xim[r];
         W1s[(2 * r + 1) * LD + 2 * lane + 1] = xre[r];
-        L1c[(lane * MC + r) * 2] = lre[r];  // row `lane` of L1
-        L1c[(lane * MC + r) * 2 + 1] = lim[r];
       }
     }
   }
@@ -697,15 +809,18 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
       double gr[MP], l2[MP], invd, x[MP];
 #pragma unroll
       for (int j = 0; j < MP; ++j) gr[j] = (lane < M && j < M) ? G[lane * LD + j] : (lane == j ? 1.0 : 0.0);
-      ok = lqc_cholesky<MP>(gr, l2, invd, lane, M);
-      lqc_tri_inverse<MP>(l2, invd, x, lane);
+      ok = lqc_cholesky_s<MP>(gr, l2, invd, lane, M, scr);
       __syncwarp();
       if (lane < MP) {
 #pragma unroll
-        for (int r = 0; r < MP; ++r) {
-          W2s[r * LD + lane] = x[r];
-          G[lane * LD + r] = l2[r];  // L2 takes the Gram matrix's place
-        }
+        for (int r = 0; r < MP; ++r) G[lane * LD + r] = l2[r];  // L2 takes the Gram matrix's place
+        dinv[lane] = invd;
+      }
+      __syncwarp();
+      lqc_tri_inverse_s<MP>(G, LD, dinv, x, lane);
+      if (lane < MP) {
+#pragma unroll
+        for (int r = 0; r < MP; ++r) W2s[r * LD + lane] = x[r];
       }
     }
     __syncwarp();
@@ -743,14 +858,21 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
         gre[j] = in ? G[r2 * LD + 2 * j] + G[(r2 + 1) * LD + 2 * j + 1] : (lane == j ? 1.0 : 0.0);
         gim[j] = in ? G[(r2 + 1) * LD + 2 * j] - G[r2 * LD + 2 * j + 1] : 0.0;
       }
-      ok = lqc_cholesky_cx<MC>(gre, gim, lre, lim, invd, lane, M);
-      lqc_tri_inverse_cx<MC>(lre, lim, invd, xre, xim, lane);
+      ok = lqc_cholesky_cx_s<MC>(gre, gim, lre, lim, invd, lane, M, scr);
       __syncwarp();
       if (lane < MC) {
 #pragma unroll
         for (int r = 0; r < MC; ++r) {
           L2c[(lane * MC + r) * 2] = lre[r];
           L2c[(lane * MC + r) * 2 + 1] = lim[r];
+        }
+        dinv[lane] = invd;
+      }
+      __syncwarp();
+      lqc_tri_inverse_cx_s<MC>(L2c, dinv, xre, xim, lane);
+      if (lane < MC) {
+#pragma unroll
+        for (int r = 0; r < MC; ++r) {
           W2c[(r * MC + lane) * 2] = xre[r];  // column `lane` of W2
           W2c[(r * MC + lane) * 2 + 1] = xim[r];
         }
