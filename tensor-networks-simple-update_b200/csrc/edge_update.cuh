@@ -85,6 +85,7 @@ struct EdgeLaunch {
   int svdw_tb_off;           // V-free variant: offset (doubles, from the group's base) of the transpose buffer + pivot column
   int smem_lq, smem_svd, smem_rc;
   int svd_vfree;             // shared-memory SVD kernel: iterate A alone, recover the kept right vectors from the initial A afterwards
+  int svd_precond;           // shared-memory SVD kernel (V-free only): pivoted Householder QR first, Jacobi on R^H
   int svd_max_sweeps;        // Jacobi sweep limit (60 for the warp kernel, 40 for the shared-memory one; TNSU_SVD_MAX_SWEEPS overrides: tests)
   int *status;               // [2] device failure counters: [0] != 0 once a theta had no finite positive singular-value sum
                              // (NaN / Inf in the state), [1] Jacobi iterations that hit their sweep limit
@@ -987,9 +988,9 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
   const bool v_on_l = !vfree && (size_t)p.ldv * p.ldv <= (size_t)2 * ldm * ldm;
   S *svdV = v_on_l ? Li : svdA + (size_t)p.lda * p.ldv;  // nc <= ldv columns
   S *A0 = svdA + (size_t)p.lda * p.ldv;                  // V-free: [nc][lda] like A
-  S *Wk = A0 + (size_t)p.lda * p.ldv;                    // V-free: [Dnew][ldv]
+  S *Wk = A0 + (size_t)p.lda * p.ldv;                    // V-free: [Dnew][lda]
   double *sig = (double *)(svdA + (size_t)p.lda * p.ldv +
-                           (vfree ? (size_t)p.lda * p.ldv + (size_t)p.dcap * p.ldv : (v_on_l ? 0 : (size_t)p.ldv * p.ldv)));
+                           (vfree ? (size_t)p.lda * p.ldv + (size_t)p.dcap * p.lda : (v_on_l ? 0 : (size_t)p.ldv * p.ldv)));
   double *lam_old = sig + TNSU_MAX_SVD;
   int *order = (int *)(lam_old + TNSU_MAX_SVD);
   int *flag = order + TNSU_MAX_SVD;
@@ -1044,13 +1045,125 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
   if (vfree) {
     for (int idx = tid; idx < nc * p.lda; idx += nthr) A0[idx] = svdA[idx];
   }
-  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40), !vfree);
+  // Preconditioner (Drmac-Veselic, as in svd_warp.cuh): Householder QR with column pivoting A = Q R~ (columns stay in
+  // place, R~ = R P^T), then the Jacobi iteration runs on X = R~^H (nc x nc), whose columns are graded: 13 -> ~8 sweeps.
+  // With the V-free recovery Q is never needed: X W = Y gives the nc-side singular vectors of A as the normalised
+  // columns of Y (row index = A's own column index), and the nr-side ones are recovered as A0 y / ||A0 y|| below.
+  const bool precond = vfree && p.svd_precond != 0;
+  int nr_it = nr;  // rows of the matrix the Jacobi iteration sees
+  if (precond) {
+    double *cn = sig;        // trailing squared column norms (sig / order are free until the iteration is over)
+    int *step_of = order;    // the step at which a column became the pivot, -1 while it waits
+    S *wv = Wk;              // the current reflector (Wk is free until the recovery)
+    __syncthreads();
+    for (int c = tid; c < nc; c += nthr) {
+      double a = 0.0;
+      for (int r = 0; r < nr; ++r) a += abs2(svdA[(size_t)c * p.lda + r]);
+      cn[c] = a;
+      step_of[c] = -1;
+    }
+    const int lane = tid & 31, wid = tid >> 5;
+    __syncthreads();
+    for (int k = 0; k < nc; ++k) {
+      if (wid == 0) {
+        // pivot = the waiting column with the largest trailing norm (ties: lowest index)
+        double best = -1.0;
+        int bi = 0;
+        for (int c = lane; c < nc; c += 32)
+          if (step_of[c] < 0 && cn[c] > best) {
+            best = cn[c];
+            bi = c;
+          }
+#pragma unroll
+        for (int mm = 16; mm >= 1; mm >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, mm);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, mm);
+          if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+          }
+        }
+        S *ap = svdA + (size_t)bi * p.lda;
+        double n2 = 0.0;
+        for (int r = k + lane; r < nr; r += 32) n2 += abs2(ap[r]);
+#pragma unroll
+        for (int mm = 16; mm >= 1; mm >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, mm);
+        const S alpha = ap[k];
+        __syncwarp();
+        double tau = 0.0;
+        if (n2 > 0.0) {
+          const double norm = sqrt(n2);
+          const double absa = sqrt(abs2(alpha));
+          const S phase = (absa > 0.0) ? alpha * (1.0 / absa) : from_real<S>(1.0);
+          tau = 1.0 / (norm * (norm + absa));
+          for (int r = k + 1 + lane; r < nr; r += 32) {
+            wv[r] = ap[r];
+            ap[r] = from_real<S>(0.0);
+          }
+          if (lane == 0) {
+            wv[k] = alpha + phase * norm;
+            ap[k] = -(phase * norm);
+          }
+        }
+        if (lane == 0) {
+          step_of[bi] = k;
+          flag[1] = bi;
+          ((volatile double *)cn)[bi] = tau;  // the pivot's norm slot is free now: carries tau to the other warps
+        }
+      }
+      __syncthreads();
+      {
+        const int piv = flag[1];
+        const double tau = cn[piv];
+        if (tau != 0.0) {
+          const int lane8 = tid & (SVD_LPP - 1), group = tid / SVD_LPP, ngroups = nthr / SVD_LPP;
+          const unsigned gmask = 0xFFu << (8 * ((tid & 31) >> 3));
+          for (int c0 = 0; c0 < nc; c0 += ngroups) {  // every lane of a warp takes part in the shuffles of each trip
+            const int c = c0 + group;
+            const bool live = c < nc && step_of[c < nc ? c : 0] < 0;
+            S *ac = svdA + (size_t)(c < nc ? c : 0) * p.lda;
+            S dot = from_real<S>(0.0);
+            if (live)
+              for (int r = k + lane8; r < nr; r += SVD_LPP) fma_acc(dot, cj(wv[r]), ac[r]);
+#pragma unroll
+            for (int mm = SVD_LPP / 2; mm >= 1; mm >>= 1) dot = dot + shfl_xor(dot, mm, gmask);
+            const S f = dot * tau;
+            double trail = 0.0;
+            if (live)
+              for (int r = k + lane8; r < nr; r += SVD_LPP) {
+                S v = ac[r];
+                fms_acc(v, f, wv[r]);
+                ac[r] = v;
+                if (r > k) trail += abs2(v);
+              }
+#pragma unroll
+            for (int mm = SVD_LPP / 2; mm >= 1; mm >>= 1) trail += __shfl_xor_sync(gmask, trail, mm);
+            if (live && lane8 == 0) cn[c] = trail;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // X = R~^H in place: conjugate transpose of the top nc x nc block; entries below a column's pivot row are exact zeros
+    for (int idx = tid; idx < nc * nc; idx += nthr) {
+      const int i = idx / nc, c = idx - i * nc;
+      if (i <= c) {
+        const S a = (i <= step_of[c]) ? svdA[(size_t)c * p.lda + i] : from_real<S>(0.0);  // R~[i][c]
+        const S bq = (c <= step_of[i]) ? svdA[(size_t)i * p.lda + c] : from_real<S>(0.0);  // R~[c][i]
+        svdA[(size_t)i * p.lda + c] = cj(a);  // X[c][i]
+        svdA[(size_t)c * p.lda + i] = cj(bq);  // X[i][c]
+      }
+    }
+    nr_it = nc;
+    __syncthreads();
+  }
+  const int svd_sweeps = jacobi_svd<S, RPL, RPL>(svdA, p.lda, nr_it, nc, svdV, p.ldv, flag, tid, nthr, min(p.svd_max_sweeps, 40), !vfree);
   long long clk2 = clock64();
 
   // singular values, descending order
   for (int j = tid; j < nc; j += nthr) {
     double s2 = 0.0;
-    for (int i = 0; i < nr; ++i) s2 += abs2(svdA[(size_t)j * p.lda + i]);
+    for (int i = 0; i < nr_it; ++i) s2 += abs2(svdA[(size_t)j * p.lda + i]);
     sig[j] = sqrt(s2);
   }
   __syncthreads();
@@ -1079,53 +1192,67 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     p.edge_err[(size_t)b * p.m_edges + ek] = (Dnew == Dk) ? sqrt(err2) : nan("");
   }
   if (vfree) {
-    // w_x[c] = sum_r conj(A0[r][c]) u_x[r],  u_x = (column order[x] of the final A) / sigma_x
-    for (int idx = tid; idx < Dnew * nc; idx += nthr) {
-      const int xp = idx / nc, c = idx - xp * nc;
+    // without preconditioner: w_x[c] = sum_r conj(A0[r][c]) u_x[r], u_x = (column order[x] of the final A) / sigma_x
+    // (nc entries); with it the iteration delivered the nc-side vectors y_x and the nr-side ones are recovered:
+    // w_x[r] = sum_c A0[r][c] y_x[c] / sigma_x (nr entries)
+    const int nw = precond ? nr : nc;  // length of the recovered vectors
+    for (int idx = tid; idx < Dnew * nw; idx += nthr) {
+      const int xp = idx / nw, c = idx - xp * nw;
       const int oc = order[xp];
-      const S *a0 = A0 + (size_t)c * p.lda, *ax = svdA + (size_t)oc * p.lda;
+      const S *ax = svdA + (size_t)oc * p.lda;
       S acc0 = from_real<S>(0.0), acc1 = from_real<S>(0.0);
-      int r = 0;
-      for (; r + 1 < nr; r += 2) {
-        fma_acc(acc0, cj(a0[r]), ax[r]);
-        fma_acc(acc1, cj(a0[r + 1]), ax[r + 1]);
+      if (precond) {
+        const S *a0 = A0 + c;  // row c of A0
+        int q = 0;
+        for (; q + 1 < nc; q += 2) {
+          fma_acc(acc0, a0[(size_t)q * p.lda], ax[q]);
+          fma_acc(acc1, a0[(size_t)(q + 1) * p.lda], ax[q + 1]);
+        }
+        if (q < nc) fma_acc(acc0, a0[(size_t)q * p.lda], ax[q]);
+      } else {
+        const S *a0 = A0 + (size_t)c * p.lda;
+        int r = 0;
+        for (; r + 1 < nr; r += 2) {
+          fma_acc(acc0, cj(a0[r]), ax[r]);
+          fma_acc(acc1, cj(a0[r + 1]), ax[r + 1]);
+        }
+        if (r < nr) fma_acc(acc0, cj(a0[r]), ax[r]);
       }
-      if (r < nr) fma_acc(acc0, cj(a0[r]), ax[r]);
       const double sv = sig[oc];
-      Wk[(size_t)xp * p.ldv + c] = (acc0 + acc1) * (sv > 0.0 ? 1.0 / sv : 0.0);
+      Wk[(size_t)xp * p.lda + c] = (acc0 + acc1) * (sv > 0.0 ? 1.0 / sv : 0.0);
     }
     __syncthreads();
     // two passes of modified Gram-Schmidt in rank order; warp w projects the vectors j + 1 + w, j + 1 + w + nwarps, ...
     const int lane = tid & 31, wid = tid >> 5, nwarps = nthr >> 5;
     for (int pass = 0; pass < 2; ++pass) {
       for (int j = 0; j < Dnew; ++j) {
-        S *wj = Wk + (size_t)j * p.ldv;
+        S *wj = Wk + (size_t)j * p.lda;
         if (wid == 0) {
           double n2 = 0.0;
-          for (int c = lane; c < nc; c += 32) n2 += abs2(wj[c]);
+          for (int c = lane; c < nw; c += 32) n2 += abs2(wj[c]);
 #pragma unroll
           for (int mm = 16; mm >= 1; mm >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, mm);
           if (!(n2 > 1e-280)) {
             // no direction of its own (sigma = 0, or A0^H u underflows): a fixed dense start vector, as in svd_warp.cuh
-            for (int c = lane; c < nc; c += 32)
+            for (int c = lane; c < nw; c += 32)
               wj[c] = from_real<S>((double)(((unsigned)(c + 1) * 2654435761u ^ (unsigned)(j + 1) * 40503u) >> 8 & 0xffffu) - 32767.5);
             __syncwarp();
             n2 = 0.0;
-            for (int c = lane; c < nc; c += 32) n2 += abs2(wj[c]);
+            for (int c = lane; c < nw; c += 32) n2 += abs2(wj[c]);
 #pragma unroll
             for (int mm = 16; mm >= 1; mm >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, mm);
           }
           const double sc = rsqrt(n2);
-          for (int c = lane; c < nc; c += 32) wj[c] = wj[c] * sc;
+          for (int c = lane; c < nw; c += 32) wj[c] = wj[c] * sc;
         }
         __syncthreads();
         for (int i = j + 1 + wid; i < Dnew; i += nwarps) {
-          S *wi = Wk + (size_t)i * p.ldv;
+          S *wi = Wk + (size_t)i * p.lda;
           S dot = from_real<S>(0.0);
-          for (int c = lane; c < nc; c += 32) fma_acc(dot, cj(wj[c]), wi[c]);
+          for (int c = lane; c < nw; c += 32) fma_acc(dot, cj(wj[c]), wi[c]);
 #pragma unroll
           for (int mm = 16; mm >= 1; mm >>= 1) dot = dot + shfl_xor(dot, mm);
-          for (int c = lane; c < nc; c += 32) fms_acc(wi[c], dot, wj[c]);
+          for (int c = lane; c < nw; c += 32) fms_acc(wi[c], dot, wj[c]);
         }
         __syncthreads();
       }
@@ -1140,8 +1267,11 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     const double sv = sig[oc];
     const double isv = sv > 0.0 ? 1.0 / sv : 0.0;
     const int trow = qi * d + ip;
-    const S vval = vfree ? Wk[(size_t)xp * p.ldv + trow] : svdV[(size_t)oc * p.ldv + trow];
-    rt_i[row * ldm + qi] = transposed ? vval : svdA[(size_t)oc * p.lda + trow] * isv;
+    // the iterated matrix carries the nr-side index without the preconditioner and the nc-side index with it; the other
+    // side is the recovered (V-free) or accumulated vector
+    const S aval = svdA[(size_t)oc * p.lda + trow] * isv;
+    const S vval = vfree ? Wk[(size_t)xp * p.lda + trow] : svdV[(size_t)oc * p.ldv + trow];
+    rt_i[row * ldm + qi] = (transposed != precond) ? vval : aval;
   }
   for (int idx = tid; idx < d * Dnew * Kj; idx += nthr) {
     const int row = idx / Kj, qj = idx - row * Kj;
@@ -1150,8 +1280,9 @@ __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_ker
     const double sv = sig[oc];
     const double isv = sv > 0.0 ? 1.0 / sv : 0.0;
     const int tcol = jp * Kj + qj;
-    const S vval = vfree ? Wk[(size_t)xp * p.ldv + tcol] : svdV[(size_t)oc * p.ldv + tcol];
-    rt_j[row * ldm + qj] = transposed ? cj(svdA[(size_t)oc * p.lda + tcol] * isv) : cj(vval);
+    const S aval = svdA[(size_t)oc * p.lda + tcol] * isv;
+    const S vval = vfree ? Wk[(size_t)xp * p.lda + tcol] : svdV[(size_t)oc * p.ldv + tcol];
+    rt_j[row * ldm + qj] = (transposed != precond) ? cj(aval) : cj(vval);
   }
   if (p.dbg_info != nullptr && b == p.dbg_point) {
     for (int j = tid; j < nc; j += nthr) p.dbg_sigma[j] = sig[order[j]];

@@ -335,7 +335,7 @@ static int plan_sweep(tnsu_engine *e) {
     }
     c.svd_vfree = e->svd_accumulate_v ? 0 : 1;
     c.smem_svd = (2 * ldm2 + e->d4 + c.lda * c.ldv +
-                  (c.svd_vfree ? c.lda * c.ldv + e->dcap * c.ldv : (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv))) * ssz +
+                  (c.svd_vfree ? c.lda * c.ldv + e->dcap * c.lda : (c.ldv * c.ldv <= 2 * ldm2 ? 0 : c.ldv * c.ldv))) * ssz +
                  2 * TNSU_MAX_SVD * 8 + TNSU_MAX_SVD * 4 + 64;
     if (c.svd_vfree && c.smem_svd > SMEM_LIMIT) {  // the accumulating variant needs less shared memory for very large thetas
       c.svd_vfree = 0;
@@ -564,6 +564,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
     p.lqc_force_fallback = e->lqc_force_fallback ? 1 : (e->lqc_cta_kernel ? 2 : 0);
     p.svdw_accv = c.svdw_accv;
     p.svd_vfree = c.svd_vfree;
+    p.svd_precond = e->svd_precond ? 1 : 0;
     p.svdw_tb_off = c.svdw_tb_off;
     p.status = e->d_status;
     p.svd_max_sweeps = e->svd_max_sweeps;
