@@ -230,7 +230,7 @@ struct __align__(16) PgLeg {  // one environment leg: dimension, 2^32/dim rounde
 
 static inline int pair_dmma_smem_bytes(int MB, int d4) {
   const int MP = 8 * MB;
-  return 2 * MP * MP * 8 + 2 * PG_CHUNK * 16 + 2 * TNSU_MAX_LEGS * 16 + 2 * TNSU_MAX_LEGS * PG_WL * 8 + MP * 8 + d4 * 8 + 64;
+  return 2 * MP * (MP + 1) * 8 + 2 * PG_CHUNK * 16 + 2 * TNSU_MAX_LEGS * 16 + 2 * TNSU_MAX_LEGS * PG_WL * 8 + MP * 8 + d4 * 8 + 64;
 }
 
 template <int MB>
@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THRE
   PgCol *cols = (PgCol *)smem_raw;                           // [2][PG_CHUNK]
   PgLeg *legs = (PgLeg *)(cols + 2 * PG_CHUNK);              // [2][legs]: environment legs, innermost first
   double *gram = (double *)(legs + 2 * TNSU_MAX_LEGS);       // [2][MP][MP]
-  double *wsq = gram + 2 * MP * MP;                          // [2][legs][PG_WL] squared weights, same order as `legs`
+  constexpr int GLD = MP + 1;  // odd leading dimension of the two Gram matrices: the mirror store and the (e, f) reads of the
+                               // contraction were 8-way / 2-way bank conflicts with GLD = MP (ncu r02: 34.5 M of 92.8 M wavefronts)
+  double *wsq = gram + 2 * MP * GLD;                          // [2][legs][PG_WL] squared weights, same order as `legs`
   double *lamrow = wsq + 2 * TNSU_MAX_LEGS * PG_WL;          // [MP] lambda_k of the bond index of row r
   double *rho = lamrow + MP;                                 // [d4]
   double *red = rho + p.d4;
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THRE
   // sum the four partial fragments of each side in warp order; tile (I,J) element [g][2t+{0,1}]
   int *modes = (int *)(red + 1);  // [2] fetch mode of each side (for the symmetric fill below)
   if (lane == 0 && q == 0) modes[side] = mode;
-  double *gs = gram + side * MP * MP;
+  double *gs = gram + side * MP * GLD;
   for (int wv = 0; wv < PG_WPS; ++wv) {
     __syncthreads();
     if (q == wv) {
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THRE
           const int r = (mode == 2) ? g * MB + I : 8 * I + g;
           const int ca = (mode == 2) ? (2 * t) * MB + J : 8 * J + 2 * t;
           const int cb = (mode == 2) ? (2 * t + 1) * MB + J : 8 * J + 2 * t + 1;
-          double *da = gs + r * MP + ca, *db = gs + r * MP + cb;
+          double *da = gs + r * GLD + ca, *db = gs + r * GLD + cb;
           double xa = 0.0, xb = 0.0;
           if (wv != 0) {
             xa = *da;
@@ -523,26 +525,27 @@ __global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THRE
     const bool m2 = modes[sdx] == 2;
     const int br = m2 ? r % MB : r >> 3, bc = m2 ? c % MB : c >> 3;  // row-block ids: only blocks I >= J were computed
     if (br >= bc) {
-      double v = gram[idx];
+      double *gp = gram + sdx * MP * GLD;
+      double v = gp[r * GLD + c];
       if (sdx) v *= lamrow[r] * lamrow[c];
-      gram[idx] = v;
-      if (br > bc) gram[sdx * MP * MP + c * MP + r] = v;
+      gp[r * GLD + c] = v;
+      if (br > bc) gp[c * GLD + r] = v;
     }
   }
   __syncthreads();
 
   // rho[i,j,i',j'] = sum_{e,f} G_i[(i,e),(i',f)] (lam_e lam_f G_j[(j,e),(j',f)]): one warp per entry, lanes over (e,f)
-  const double *gi = gram, *gj = gram + MP * MP;
-  int eo[8];  // (e,f) pairs of this lane as offsets e*MP + f; Dk <= 16 -> at most 8 per lane
+  const double *gi = gram, *gj = gram + MP * GLD;
+  int eo[8];  // (e,f) pairs of this lane as offsets e*GLD + f; Dk <= 16 -> at most 8 per lane
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ef = lane + 32 * k;
     const int e = ef / Dk, f = ef - e * Dk;
-    eo[k] = ef < Dk * Dk ? e * MP + f : -1;
+    eo[k] = ef < Dk * Dk ? e * GLD + f : -1;
   }
   for (int idx = warp; idx < p.d4; idx += PG_THREADS / 32) {
     const int jp = idx % d, ip = (idx / d) % d, j = (idx / (d * d)) % d, i = idx / (d * d * d);
-    const double *bi = gi + (i * Dk) * MP + ip * Dk, *bj = gj + (j * Dk) * MP + jp * Dk;
+    const double *bi = gi + (i * Dk) * GLD + ip * Dk, *bj = gj + (j * Dk) * GLD + jp * Dk;
     double a = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
