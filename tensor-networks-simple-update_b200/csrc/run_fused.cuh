@@ -462,25 +462,31 @@ DEV double fused_recompose_regs(const FusedLaunch &p, const FusedWarp &wm, const
   return 1.0 / sqrt(n2);
 }
 
-// one imaginary-time-evolution step on edge ek (reference :219-296), executed by one warp
+// one imaginary-time-evolution step on edge ek (reference :219-296), executed by one warp (or shared by two)
+// `wm` is the work area that holds the edge's data (L, S, r~, the staged bond matrices, the SVD group memory); `own` is the
+// calling warp's scratch (Z / T / pivot column / row offsets).  role 0: this warp does the whole update (wm == own).
+// roles 1 / 2: the level has ONE edge and two warps share it — warp 0 (role 1) takes side 0 and the SVD, warp 1 (role 2)
+// takes side 1; the three phases are separated by block barriers that every warp of the CTA executes.
 template <int R, int MMAX, int CPL, bool ACCV>
-DEV void fused_edge_update(const FusedLaunch &p, const EdgeDesc *descs, const FusedWarp &wm, double *tens, double *wts, double *iwts,
-                           double *tsc, double *eerr, int b, int ek, int slot, int lane) {
+DEV void fused_edge_update(const FusedLaunch &p, const EdgeDesc *descs, const FusedWarp &wm, const FusedWarp &own, int role,
+                           double *tens, double *wts, double *iwts, double *tsc, double *eerr, int b, int ek, int slot, int lane) {
   const EdgeDesc &ed = descs[ek];
   const int ldm2 = p.ldm * p.ldm;
   double *L[2] = {wm.gs, wm.gs + ldm2};
   const bool prof = p.prof != nullptr && b == 0 && (threadIdx.x >> 5) == 0 && lane == 0;
+  const bool mine[2] = {role != 2, role != 1};  // the sides this warp reduces and recomposes
   long long c0 = clock64();
   for (int side = 0; side < 2; ++side) {
+    if (!mine[side]) continue;
     const SideDesc &sd = ed.s[side];
     long long c1;
     if constexpr (MMAX > 0) {
       c1 = c0;
-      fused_lq_regs<MMAX, CPL>(p, wm, sd, ed.Dk, tens + p.toff[sd.tensor], wts, tsc[sd.tensor], wm.Pd[side], L[side], wm.S[side], lane);
+      fused_lq_regs<MMAX, CPL>(p, own, sd, ed.Dk, tens + p.toff[sd.tensor], wts, tsc[sd.tensor], wm.Pd[side], L[side], wm.S[side], lane);
     } else {
-      fused_stage(p, sd, ed.Dk, tens + p.toff[sd.tensor], wts, tsc[sd.tensor], wm.Pd[side], wm.rowoff, lane);
+      fused_stage(p, sd, ed.Dk, tens + p.toff[sd.tensor], wts, tsc[sd.tensor], wm.Pd[side], own.rowoff, lane);
       c1 = clock64();
-      fused_lq(p, wm, wm.Pd[side], sd.M, sd.N, sd.K, L[side], wm.S[side], lane);
+      fused_lq(p, own, wm.Pd[side], sd.M, sd.N, sd.K, L[side], wm.S[side], lane);
     }
     const long long c2 = clock64();
     if (prof) {
@@ -489,6 +495,8 @@ DEV void fused_edge_update(const FusedLaunch &p, const EdgeDesc *descs, const Fu
     }
     c0 = c2;
   }
+  if (role != 0) bar_sync(1, blockDim.x);  // both L factors are in the edge's work area
+  if (role != 2) {
   const double *gate_src = p.gates + (size_t)slot * p.gate_slot_stride + ((size_t)b * p.m_edges + ek) * p.d4;
   int theta_ready = 0;
   if (p.svd_precond) {
@@ -573,20 +581,23 @@ DEV void fused_edge_update(const FusedLaunch &p, const EdgeDesc *descs, const Fu
     if (prof) p.prof[2] += c1 - c0;
     c0 = c1;
   }
+  }  // role != 2
+  if (role != 0) bar_sync(1, blockDim.x);  // r~_i, r~_j, lambda' and its reciprocals are complete
   for (int side = 0; side < 2; ++side) {
+    if (!mine[side]) continue;
     const SideDesc &sd = ed.s[side];
     // row offsets of this side (the staging of side 1 overwrote those of side 0)
     if (lane < 32) {
       const int r = lane < sd.Mout ? lane : 0;
       const int s = r / ed.Dnew, x = r - s * ed.Dnew;
-      wm.rowoff[lane] = (int)(s * sd.out_stride_phys + x * sd.out_stride[sd.bond_leg]);
+      own.rowoff[lane] = (int)(s * sd.out_stride_phys + x * sd.out_stride[sd.bond_leg]);
     }
     __syncwarp();
     double sc;
     if constexpr (MMAX > 0)
-      sc = fused_recompose_regs<MMAX, CPL>(p, wm, sd, wm.Pd[side], wm.Rt[side], wm.S[side], tens + p.toff[sd.tensor], iwts, lane);
+      sc = fused_recompose_regs<MMAX, CPL>(p, own, sd, wm.Pd[side], wm.Rt[side], wm.S[side], tens + p.toff[sd.tensor], iwts, lane);
     else
-      sc = fused_recompose(p, wm, sd, wm.Pd[side], wm.Rt[side], wm.S[side], tens + p.toff[sd.tensor], iwts, lane);
+      sc = fused_recompose(p, own, sd, wm.Pd[side], wm.Rt[side], wm.S[side], tens + p.toff[sd.tensor], iwts, lane);
     if (lane == 0) tsc[sd.tensor] = sc;
     __syncwarp();
   }
@@ -659,6 +670,7 @@ __global__ void __launch_bounds__(32 * FUSED_MAX_WARPS) run_fused_kernel(const F
   int *ctrl = (int *)(pval + m);
   double *warp_base = pval + m + 8;
   const FusedWarp wm = fused_warp_mem(p, warp_base + (size_t)warp * p.warp_doubles);
+  const FusedWarp wm0 = fused_warp_mem(p, warp_base);  // warp 0's area: the edge data of a level whose single edge two warps share
   const EdgeDesc *descs = p.descs;
   if (p.descs_in_smem) {
     unsigned long long *dst = (unsigned long long *)(warp_base + (size_t)p.n_warps * p.warp_doubles);
@@ -692,7 +704,19 @@ __global__ void __launch_bounds__(32 * FUSED_MAX_WARPS) run_fused_kernel(const F
   for (;;) {
     for (int lv = 0; lv < p.n_levels; ++lv) {
       const int e0 = p.level_off[lv], e1 = p.level_off[lv + 1];
-      for (int ei = e0 + warp; ei < e1; ei += p.n_warps) fused_edge_update<R, MMAX, CPL, ACCV>(p, descs, wm, tens, wts, iwts, tsc, eerr, b, p.level_edges[ei], slot, lane);
+      if (e1 - e0 == 1 && p.n_warps >= 2) {
+        // a level with ONE edge: its two sides go to warps 0 and 1 (each reduces and recomposes one site tensor, warp 0
+        // runs the SVD in between); the other warps only take part in the two phase barriers
+        if (warp < 2) {
+          fused_edge_update<R, MMAX, CPL, ACCV>(p, descs, wm0, wm, warp + 1, tens, wts, iwts, tsc, eerr, b, p.level_edges[e0], slot, lane);
+        } else {
+          bar_sync(1, blockDim.x);
+          bar_sync(1, blockDim.x);
+        }
+      } else {
+        for (int ei = e0 + warp; ei < e1; ei += p.n_warps)
+          fused_edge_update<R, MMAX, CPL, ACCV>(p, descs, wm, wm, 0, tens, wts, iwts, tsc, eerr, b, p.level_edges[ei], slot, lane);
+      }
       const long long cb0 = clock64();
       __syncthreads();
       if (p.prof != nullptr && b == 0 && tid == 0) p.prof[5] += clock64() - cb0;

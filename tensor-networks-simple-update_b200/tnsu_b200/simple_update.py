@@ -312,10 +312,10 @@ class SimpleUpdateBatch:
         for p in range(self.n_points):
             k = int(res["n_checks"][p])
             loggers.append({
-                "error": [float(x) for x in res["log_error"][p, :k]],
-                "dt": [self.dts[p][int(s)] for s in res["log_slot"][p, :k]],
-                "iteration": [int(x) for x in res["log_step"][p, :k]],
-                "energy": [float(x) for x in res["log_energy"][p, :k]],
+                "error": res["log_error"][p, :k].tolist(),
+                "dt": [self.dts[p][s] for s in res["log_slot"][p, :k].tolist()],
+                "iteration": res["log_step"][p, :k].tolist(),
+                "energy": res["log_energy"][p, :k].tolist(),
                 "converged": bool(res["converged"][p]),
                 "sweeps": int(res["sweeps"][p]),
                 "final_dt": self.dts[p][int(res["final_slot"][p])],
