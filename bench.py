@@ -109,6 +109,61 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's threads (and with them the first-touch placement of its pinned host buffers) to the CPUs NVML lists
+    as local to its GPU: with 8 ranks the uploads of one rank otherwise cross the socket interconnect.  Instrumentation
+    only; returns the number of CPUs bound to, or None when NVML / the affinity call is not available."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0")
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001 - best effort
+        pass
+    return None
+
+
+def link_rates(torch, barrier, nbytes=512 << 20, reps=3):
+    """Pinned-memory copy rates of THIS rank while every rank copies at the same time (GB/s: up alone, down alone, both
+    directions together): what the host side can feed, next to what the e2e leg gets out of it."""
+    h_up = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_dn = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down):
+        def once():
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_a.copy_(h_up, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_b, non_blocking=True)
+
+        once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return (int(up) + int(down)) * nbytes * reps / dt / 1e9
+
+    return run(True, False), run(False, True), run(True, True)
+
+
 def seeded_networks(batch, first_seed=0):
     """Host state exactly as TensorNetwork.__init__ draws it (legacy global numpy stream, seed b for network b)."""
     import tnsu_b200 as tnsu
@@ -322,6 +377,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -484,6 +540,7 @@ def run_gpu_arm(args):
     e2e_run(args.e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    link = link_rates(torch, barrier)  # all ranks copy at the same time, like in the e2e leg above
     h2d = sum(t.nbytes for t in host_t) + N_E * host_w.nbytes
     d2h = out_e.nbytes + sum(w.nbytes for w in out_w) + sum(t.nbytes for t in out_t)
     assert all(abs(np.linalg.norm(out_t[0][b]) - 1.0) < 1e-9 for b in (0, batch - 1))  # the sweep's tensors did come back
@@ -516,9 +573,12 @@ def run_gpu_arm(args):
     vals = [ms, e2e_s * 1e3, energy_ms, converged["ms"] if converged else 0.0, c128["ms"] if c128 else 0.0,
             e2e_whole["seconds"] * 1e3 if e2e_whole else 0.0]
     times = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    link_sum = torch.tensor(link, dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(link_sum, op=dist.ReduceOp.SUM)
     ms, e2e_ms, energy_ms, conv_ms, c128_ms, whole_ms = (float(x) for x in times.cpu())
+    link_up, link_down, link_both = (float(x) for x in link_sum.cpu())
     edges_per_step = world * batch * N_E
     value = edges_per_step * args.steps / (ms * 1e-3)
     e2e_value = edges_per_step * args.e2e_steps / (e2e_ms * 1e-3)
@@ -561,6 +621,11 @@ def run_gpu_arm(args):
                        "parallelism": f"points sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "chunks": n_ch,
+                    "link_gbs": (h2d + d2h) * world * args.e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                    "host_link": {"up_gbs": link_up, "down_gbs": link_down, "both_directions_gbs": link_both, "unit": "GB/s",
+                                  "numa_bound_cpus_rank0": numa_cpus,
+                                  "what": "pinned-memory copies of 512 MiB per direction, all ranks at the same time, summed over "
+                                          "the ranks: the ceiling of `link_gbs`, the bytes this leg moves per second in both directions"},
                     "what": "per step: upload all networks from pinned host memory + 1 sweep + download EVERYTHING the sweep produced "
                             "(all tensors, all weights, the convergence error), through the C ABI; the batch is split over `chunks` "
                             "engines driven by one host thread each so uploads, sweeps and downloads of different chunks overlap"},

@@ -24,6 +24,7 @@
 
 #define SVDW_THREADS 128
 #define SVDW_MAX_SWEEPS 60
+#define SVDW_TRACKED_SWEEPS 12  // V-free iteration: sweeps that carry the column norms along; later ones recompute them per pair
 
 template <int R>
 struct SvdwCols {
@@ -83,23 +84,36 @@ DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (
 //   flip = false:  x' = s x + c y,  y' = c x - s y        flip = true:  x' = -s x + c y,  y' = c x + s y
 // where (c, s) come from (al, be, ga) = (|P|^2, |Q|^2, P.Q) of the ordered pair (P, Q) = flip ? (y, x) : (x, y).
 template <int R>
-DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle) {
-  double nx0 = 0.0, nx1 = 0.0, ny0 = 0.0, ny1 = 0.0, ga0 = 0.0, ga1 = 0.0;
+DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, bool flip, bool idle, bool exact) {
+  // nx, ny: the squared norms of the two columns, CARRIED ALONG (both row halves hold the same values): they are
+  // updated from the rotation below instead of being recomputed for every pair — two of the three dot products of a
+  // step.  The sweep loop refreshes them from the columns once per sweep; `exact` (warp-uniform: an iteration far
+  // beyond its usual length) recomputes them here, as the kernel did before.  Model: tools/experiments/svd_tracked_norms.py
+  // (same sweeps, same singular values on oracle thetas, on matrices graded over 30 decades and on rank-deficient ones).
+  double ga0 = 0.0, ga1 = 0.0;
 #pragma unroll
   for (int r = 0; r < R; r += 2) {
-    nx0 = fma(xa[r], xa[r], nx0);
-    ny0 = fma(ya[r], ya[r], ny0);
     ga0 = fma(xa[r], ya[r], ga0);
-    if (r + 1 < R) {
-      nx1 = fma(xa[r + 1], xa[r + 1], nx1);
-      ny1 = fma(ya[r + 1], ya[r + 1], ny1);
-      ga1 = fma(xa[r + 1], ya[r + 1], ga1);
-    }
+    if (r + 1 < R) ga1 = fma(xa[r + 1], ya[r + 1], ga1);
   }
-  double nx = nx0 + nx1, ny = ny0 + ny1, ga = ga0 + ga1;
-  nx += __shfl_xor_sync(0xffffffffu, nx, 1);
-  ny += __shfl_xor_sync(0xffffffffu, ny, 1);
+  double ga = ga0 + ga1;
   ga += __shfl_xor_sync(0xffffffffu, ga, 1);
+  if (exact) {
+    double nx0 = 0.0, nx1 = 0.0, ny0 = 0.0, ny1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      nx0 = fma(xa[r], xa[r], nx0);
+      ny0 = fma(ya[r], ya[r], ny0);
+      if (r + 1 < R) {
+        nx1 = fma(xa[r + 1], xa[r + 1], nx1);
+        ny1 = fma(ya[r + 1], ya[r + 1], ny1);
+      }
+    }
+    nx = nx0 + nx1;
+    ny = ny0 + ny1;
+    nx += __shfl_xor_sync(0xffffffffu, nx, 1);
+    ny += __shfl_xor_sync(0xffffffffu, ny, 1);
+  }
   const double al = flip ? ny : nx, be = flip ? nx : ny;
   const double tol2 = 2.25e-30;
   const double g2 = ga * ga;
@@ -126,6 +140,13 @@ DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], bool flip, bool idle)
     const double x0 = xa[r], y0 = ya[r];
     xa[r] = fma(sa, x0, c * y0);
     ya[r] = fma(c, x0, -(sa * y0));
+  }
+  // |x'|^2 = s^2 |x|^2 + c^2 |y|^2 + 2 sa c x.y,   |y'|^2 = c^2 |x|^2 + s^2 |y|^2 - 2 sa c x.y
+  {
+    const double ss = s * s, cc = c * c, m = 2.0 * c * sa * ga;
+    const double nxn = fma(ss, nx, fma(cc, ny, m));
+    ny = fma(cc, nx, fma(ss, ny, -m));
+    nx = nxn;
   }
   return kind;
 }
@@ -489,15 +510,39 @@ DEV void svdw_body(const SvdwArgs &args) {
     // for.  That sweep would rotate nothing; skipping it saves one of the ~7 sweeps of a 32 x 32 theta.  Pairs of
     // (nearly) equal singular values rotate by large angles at tiny cosines: they are not small, and the usual
     // rotation-free sweep confirms them.
+    int src_pending = lane;
     for (; sweeps < max_sweeps; ++sweeps) {
       unsigned kinds = 0u;
+      // the column norms travel with the columns and are refreshed from them once per sweep (svdw_step_a)
+      double nx, ny;
+      {
+        double nx0 = 0.0, nx1 = 0.0, ny0 = 0.0, ny1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          nx0 = fma(xa[r], xa[r], nx0);
+          ny0 = fma(ya[r], ya[r], ny0);
+          if (r + 1 < R) {
+            nx1 = fma(xa[r + 1], xa[r + 1], nx1);
+            ny1 = fma(ya[r + 1], ya[r + 1], ny1);
+          }
+        }
+        nx = nx0 + nx1;
+        ny = ny0 + ny1;
+        nx += __shfl_xor_sync(0xffffffffu, nx, 1);
+        ny += __shfl_xor_sync(0xffffffffu, ny, 1);
+      }
+      const bool exact = sweeps >= SVDW_TRACKED_SWEEPS;
 #pragma unroll 1
       for (int st = 0; st < 2 * NP; ++st) {
-        const bool flip = (st & 1) != 0;
-        kinds |= svdw_step_a<R>(xa, ya, flip, flip && last);
-        const int src = flip ? src_prev : src_next;
+        // the cyclic shift that follows a step is applied at the top of the NEXT one: the shuffled values are consumed
+        // by the rotation right away and its results land in the loop-carried registers (no register copies at the
+        // loop end).  The shift still pending when the iteration ends only decides which lane holds which column.
 #pragma unroll
-        for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src);
+        for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src_pending);
+        nx = __shfl_sync(0xffffffffu, nx, src_pending);
+        const bool flip = (st & 1) != 0;
+        kinds |= svdw_step_a<R>(xa, ya, nx, ny, flip, flip && last, exact);
+        src_pending = flip ? src_prev : src_next;
       }
       if (!__any_sync(0xffffffffu, (kinds & 2u) != 0u)) {
         ++sweeps;
