@@ -186,6 +186,42 @@ def jacobi_odd_even(x, acc, tol=1.5e-15, max_sweeps=60):
     return x, acc, max_sweeps
 
 
+def jacobi_odd_even_tracked(x, tol=1.5e-15, max_sweeps=60, exact_from=12, small=2.6e-30):
+    """The iteration of the V-free kernel route (svdw_step_a): the odd-even ordering of `jacobi_odd_even` without an
+    accumulator, with the squared column norms CARRIED ALONG (updated from each rotation, refreshed from the columns
+    once per sweep, recomputed per pair from sweep `exact_from` on), and with the exit rule of the kernel: stop after a
+    sweep without rotation, or after one whose (max cos^2 of a pair met) x (max sin^2 of a rotation applied) <= `small`.
+    Returns (x, sweeps)."""
+    x = np.array(x, dtype=float)
+    n = x.shape[1]
+    for sweep in range(max_sweeps):
+        nrm = np.sum(x * x, axis=0)
+        max_cos2 = max_sin2 = 0.0
+        for step in range(n + (n & 1)):
+            for p in range(step % 2, n - 1, 2):
+                q = p + 1
+                if sweep >= exact_from:
+                    nrm[p], nrm[q] = x[:, p] @ x[:, p], x[:, q] @ x[:, q]
+                al, be, ga = nrm[p], nrm[q], x[:, p] @ x[:, q]
+                c, s = 1.0, 0.0
+                if ga * ga > tol * tol * al * be and ga != 0.0:
+                    delta = be - al
+                    inv_r = 1.0 / np.sqrt(delta * delta + 4.0 * ga * ga)
+                    c2 = 0.5 + 0.5 * abs(delta) * inv_r
+                    c = np.sqrt(c2)
+                    s = (-ga if delta < 0 else ga) * inv_r / c
+                    max_cos2 = max(max_cos2, ga * ga / (al * be) if al * be > 0 else np.inf)
+                    max_sin2 = max(max_sin2, s * s)
+                pc, qc = x[:, p].copy(), x[:, q].copy()
+                x[:, p] = s * pc + c * qc
+                x[:, q] = c * pc - s * qc
+                m = 2.0 * c * s * ga
+                nrm[p], nrm[q] = s * s * al + c * c * be + m, c * c * al + s * s * be - m
+        if max_cos2 * max_sin2 <= small:  # includes the sweep without rotation
+            return x, sweep + 1
+    return x, max_sweeps
+
+
 def svd_preconditioned(theta):
     """theta = U diag(s) V^T the way `svd_warp_kernel` computes it: A' = theta^T, A' = Q R~ (pivoted QR),
     Jacobi on X = R~^T with the accumulator started at Q:  X W = Y  =>  A' = (Q W)(Y)^T, so the right vectors of
@@ -248,7 +284,7 @@ def svd_vfree(theta, keep):
     passes of modified Gram-Schmidt in rank order.  Returns u (n_i x keep), s (keep), w^T (keep x n_j), sweeps."""
     theta = np.array(theta, dtype=float)
     _, r_tilde = qr_column_pivoting(theta.T)
-    x, _, sweeps = jacobi_odd_even(r_tilde.T, np.zeros((1, r_tilde.shape[0])))
+    x, sweeps = jacobi_odd_even_tracked(r_tilde.T)
     sv = np.sqrt(np.sum(x * x, axis=0))
     order = np.argsort(-sv, kind="stable")[:keep]
     sv, x = sv[order], x[:, order]

@@ -84,7 +84,7 @@ DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (
 //   flip = false:  x' = s x + c y,  y' = c x - s y        flip = true:  x' = -s x + c y,  y' = c x + s y
 // where (c, s) come from (al, be, ga) = (|P|^2, |Q|^2, P.Q) of the ordered pair (P, Q) = flip ? (y, x) : (x, y).
 template <int R>
-DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, bool flip, bool idle, bool exact) {
+DEV void svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, int &max_ecos, int &max_esin, bool flip, bool idle, bool exact) {
   // nx, ny: the squared norms of the two columns, CARRIED ALONG (both row halves hold the same values): they are
   // updated from the rotation below instead of being recomputed for every pair — two of the three dot products of a
   // step.  The sweep loop refreshes them from the columns once per sweep; `exact` (warp-uniform: an iteration far
@@ -128,8 +128,12 @@ DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &n
     c = c2 * inv_c;
     s = (delta < 0.0 ? -ga : ga) * inv_r * inv_c;
   }
-  // a "small" rotation: cosine of the pair <= 1e-10 and |sin| of the rotation <= 1e-7 (see the sweep loop)
-  const unsigned kind = rot ? (((g2 <= 1e-20 * ab) && (s * s <= 1e-14)) ? 1u : 3u) : 0u;
+  // binary exponents of cos^2 = g2 / (al be) of the pair and of sin^2 of its rotation (each within 1 of log2), their
+  // maxima over the sweep decide whether a confirming sweep is needed (see the sweep loop)
+  if (rot) {
+    max_ecos = max(max_ecos, ((__double2hiint(g2) >> 20) & 0x7ff) - ((__double2hiint(ab) >> 20) & 0x7ff));
+    max_esin = max(max_esin, ((__double2hiint(s * s) >> 20) & 0x7ff) - 1023);
+  }
   if (idle) {
     c = 0.0;
     s = 1.0;
@@ -148,7 +152,6 @@ DEV unsigned svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &n
     ny = fma(cc, nx, fma(ss, ny, -m));
     nx = nxn;
   }
-  return kind;
 }
 
 // Everything one call of the warp SVD needs.  The edge-update kernel K2 (svd_warp_kernel) fills it per (point, edge)
@@ -503,16 +506,18 @@ DEV void svdw_body(const SvdwArgs &args) {
   } else {
     // one half step per trip (step A: pair (x_k, y_k), then x_k <- x_{k+1}; step B: pair (y_k, x_k), the last
     // processor idle, then x_k <- x_{k-1}): a single copy of the step in the instruction stream
-    // The iteration ends after a sweep without rotation — or after a sweep whose rotations were all SMALL: every pair
-    // met had a cosine <= 1e-10 and was rotated by |sin| <= 1e-7.  A pair made orthogonal in such a sweep is disturbed
-    // afterwards only by the later rotations of its two columns, each adding at most |sin| x (cosine of the third
-    // column) <= 1e-17, at most 2 (n - 1) times: <= 6.2e-16 at n = 32, below the 1.5e-15 a further sweep would test
-    // for.  That sweep would rotate nothing; skipping it saves one of the ~7 sweeps of a 32 x 32 theta.  Pairs of
-    // (nearly) equal singular values rotate by large angles at tiny cosines: they are not small, and the usual
-    // rotation-free sweep confirms them.
+    // The iteration ends after a sweep without rotation — or after a sweep whose rotations were all SMALL, in the sense
+    // (max cosine of a pair met) x (max |sin| of a rotation applied) <= 1.6e-15: a pair made orthogonal in such a sweep is
+    // disturbed afterwards only by the later rotations of its two columns, each adding at most |sin| x (cosine of the
+    // third column), at most 2 (n - 1) = 62 times at n = 32: the cosines left behind are <= 1e-13, the singular values
+    // (second order in them) exact to rounding and the vectors good to 1e-13 — the confirming sweep, one of the ~7 of a
+    // 32 x 32 theta, would only establish that.  Measured on oracle thetas (tools/experiments/svd_tracked_norms.py): 0.75
+    // to 0.9 sweeps saved per theta, cosines left behind <= 1.6e-15.  Pairs of (nearly) equal singular values rotate by
+    // large angles at tiny cosines: they do not pass, and the usual rotation-free sweep confirms them.
+    // The test runs on binary exponents: log2(cos^2 sin^2) < max_ecos + max_esin + 2 <= -99 < log2(2.6e-30).
     int src_pending = lane;
     for (; sweeps < max_sweeps; ++sweeps) {
-      unsigned kinds = 0u;
+      int max_ecos = -100000, max_esin = -100000;  // no rotation yet
       // the column norms travel with the columns and are refreshed from them once per sweep (svdw_step_a)
       double nx, ny;
       {
@@ -541,10 +546,10 @@ DEV void svdw_body(const SvdwArgs &args) {
         for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src_pending);
         nx = __shfl_sync(0xffffffffu, nx, src_pending);
         const bool flip = (st & 1) != 0;
-        kinds |= svdw_step_a<R>(xa, ya, nx, ny, flip, flip && last, exact);
+        svdw_step_a<R>(xa, ya, nx, ny, max_ecos, max_esin, flip, flip && last, exact);
         src_pending = flip ? src_prev : src_next;
       }
-      if (!__any_sync(0xffffffffu, (kinds & 2u) != 0u)) {
+      if (__reduce_max_sync(0xffffffffu, max_ecos) + __reduce_max_sync(0xffffffffu, max_esin) <= -101) {
         ++sweeps;
         jacobi_done = true;
         break;

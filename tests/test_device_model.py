@@ -95,6 +95,33 @@ def test_vfree_svd_route_matches_oracle(name):
         assert abs(e1 - e2) < 1e-12
 
 
+def test_tracked_norms_and_exit_rule_of_the_jacobi_iteration():
+    """svdw_step_a carries the column norms along and skips the confirming sweep when the last sweep's rotations were
+    small (device_model.jacobi_odd_even_tracked): never more sweeps than the plain iteration, at least one fewer on
+    average, columns orthogonal to 1e-13 and LAPACK's singular values — on generic, graded and rank-deficient input."""
+    rng = np.random.default_rng(11)
+    saved = []
+    for n, kind in ((32, "generic"), (32, "graded"), (32, "rank8"), (16, "generic"), (16, "graded")):
+        for _ in range(3):
+            u, _ = np.linalg.qr(rng.normal(size=(n, n)))
+            v, _ = np.linalg.qr(rng.normal(size=(n, n)))
+            sv = {"generic": rng.uniform(0.01, 1.0, n), "graded": np.logspace(0, -14, n),
+                  "rank8": np.r_[rng.uniform(0.1, 1.0, 8), np.zeros(n - 8)]}[kind]
+            a = (u * sv) @ v.T
+            _, r_tilde = dm.qr_column_pivoting(a.T)
+            _, _, plain = dm.jacobi_odd_even(r_tilde.T, np.zeros((1, n)))
+            x, sweeps = dm.jacobi_odd_even_tracked(r_tilde.T)
+            assert sweeps <= plain
+            saved.append(plain - sweeps)
+            got = np.sqrt(np.sum(x * x, axis=0))
+            ref = np.linalg.svd(a, compute_uv=False)
+            assert np.abs(np.sort(got)[::-1] - ref).max() < 1e-13 * ref[0]
+            big = got > 1e-8 * got.max()
+            g = (x[:, big] / got[big]).T @ (x[:, big] / got[big])
+            assert np.abs(g - np.eye(int(big.sum()))).max() < 1e-13
+    assert np.mean(saved) >= 0.5
+
+
 def test_vfree_svd_properties():
     """svd_vfree on graded and on exactly rank-deficient matrices: LAPACK's leading singular values, orthonormal kept
     vectors on both sides, and theta w_k = sigma_k u_k wherever sigma_k is not negligible."""
