@@ -79,6 +79,7 @@ struct tnsu_engine {
   bool plan_valid = false, plan_steady = false;
   bool lq_stream = false;                 // TNSU_LQ_STREAM=1: persistent TMA-staged K1 instead of one-shot CTAs (measured 4 % slower)
   int num_sms = 148;
+  int lq_stream_min_n = 256;              // TNSU_LQ_MIN_N: bond matrices at least this wide stream at any batch size
   bool force_unrolled_lq = false;         // TNSU_LQ=unrolled: keep the fully unrolled K1 (A/B comparisons)
   bool svd_precond = true;                // TNSU_SVD_PRECOND=0: plain Jacobi in the warp SVD (A/B comparisons)
   bool use_graphs = false;                // TNSU_GRAPH=1: replay the run-loop iteration as a CUDA graph (measured: no faster)
@@ -378,11 +379,14 @@ static int plan_sweep(tnsu_engine *e) {
       c.svdw_group_doubles = (c.svdw_group_doubles + 1) & ~1;
     }
     if (!e->force_householder && !e->force_simple_rc && !e->lq_stream && !e->force_unrolled_lq && e->dcap <= 32 &&
-        (cx ? 2 * maxM <= 32 : c.cluster == 1) && maxN >= 256) {
+        (cx ? 2 * maxM <= 32 : c.cluster == 1) &&
+        (maxN >= e->lq_stream_min_n || 2LL * e->batch * (long long)e->level_edges[lv].size() >= 16LL * e->num_sms)) {
       // streaming K1/K3: every side of the level must have M <= N, an unchanged bond dimension (the recompose runs in
       // place) and tensors below 2 GiB (32-bit byte offsets).  Narrow bond matrices (N < 256: the D <= 4 networks of the
-      // sweep metric) stay with the Householder kernels: there a launch is latency bound, and two Cholesky chains plus
-      // two more launches per level cost more than they save (measured: 570 vs 531 us per sweep at D = 4, 256 points)
+      // sweep metric) stay with the Householder kernels while a launch is latency bound — two Cholesky chains plus two
+      // more launches per level cost more than they save (measured at D = 4: 608 vs 570 us per sweep at 256 points) —
+      // and stream as soon as the launch fills the GPU (one wave of 16 warps per SM): 1.55 vs 1.86 ms per sweep at 4096
+      // points, 10.3 vs 12.7 ms at 32768
       bool ok_lqc = true;
       int mm = 1;
       for (int ek : e->level_edges[lv]) {
@@ -1062,6 +1066,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     e->lqc_force_fallback = env && std::string(env) == "fallback";
     e->lqc_cta_kernel = env && std::string(env) == "cta";
+    env = getenv("TNSU_LQ_MIN_N");
+    if (env && atoi(env) > 0) e->lq_stream_min_n = atoi(env);
     env = getenv("TNSU_FUSED");
     if (env && std::string(env) == "0") e->use_fused = false;
     if (env && std::string(env) == "force") e->force_fused = true;

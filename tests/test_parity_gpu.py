@@ -408,6 +408,54 @@ def test_batch_matches_single_and_oracle(tnsu):
             assert np.abs(a - b).max() < 1e-10
 
 
+def test_narrow_bond_matrices_stream_once_the_batch_fills_the_gpu(tnsu, monkeypatch):
+    """D = 4 bond matrices (8 x 64) stay with the Householder kernels in small batches and take the streaming
+    CholeskyQR2 K1c / in-place K3c as soon as a launch fills the GPU (2 x batch x edges of a level >= 16 warps per SM).
+    A batch of 1536 TFI networks (48 distinct seeds x fields, tiled) through whole runs: the streaming path is taken
+    (stats), every point equals the same point run alone on the Householder path to 1e-11 and the oracle to 1e-10."""
+    pz, px = np.array([[1, 0], [0, -1]]), np.array([[0, 1], [1, 0]])
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    n_distinct, reps = 48, 32
+    fields = [-0.25 - 3.5 * k / (n_distinct - 1) for k in range(n_distinct)]
+
+    def networks():
+        out = []
+        for k in range(n_distinct):
+            np.random.seed(300 + k)
+            out.append(tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=4, spin_dim=2))
+        return out
+
+    base = networks()
+    nets = [base[k % n_distinct].copy() for k in range(n_distinct * reps)]
+    big = tnsu.SimpleUpdateBatch(nets, [-1.0] * 8, tnsu.per_point([fields[k % n_distinct] for k in range(len(nets))]), [pz], [pz],
+                                 [px], [0.1, 0.01], d_max=4, max_iterations=12, convergence_error=1e-7)
+    logs = big.run()
+    e_big = big.energy_per_site()
+    st = big.engine.stats()
+    assert st["lq_streamed"] > 0 and st["fused_runs"] == 0
+    _note(f"narrow streaming: {st['lq_streamed']} (item, side)s streamed, {st['lq_flagged']} flagged, batch {len(nets)}")
+    small_nets = networks()
+    monkeypatch.setenv("TNSU_FUSED", "0")  # the general launch path (Householder K1 / K3 at this batch size)
+    small = tnsu.SimpleUpdateBatch(small_nets, [-1.0] * 8, tnsu.per_point(fields), [pz], [pz], [px], [0.1, 0.01], d_max=4,
+                                   max_iterations=12, convergence_error=1e-7)
+    logs_small = small.run()
+    e_small = small.energy_per_site()
+    assert small.engine.stats()["lq_streamed"] == 0
+    for k in range(len(nets)):
+        j = k % n_distinct
+        assert logs[k]["sweeps"] == logs_small[j]["sweeps"] and abs(e_big[k] - e_small[j]) < 1e-11
+        if k < n_distinct or k >= len(nets) - n_distinct:
+            for a, b in zip(nets[k].weights, small_nets[j].weights):
+                assert np.abs(a - b).max() < 1e-11
+    for j in (0, 17, 47):
+        model = orc.Model([-1.0] * 8, fields[j], [pz], [pz], [px])
+        ref = networks()[j]
+        t, w = [np.array(x) for x in ref.tensors], [np.array(x) for x in ref.weights]
+        log = orc.run(t, w, smat, model, [0.1, 0.01], 4, 12, 1e-7)
+        assert len(log["error"]) == len(logs[j]["error"])
+        assert abs(orc.energy_per_site(t, w, smat, model) - e_big[j]) < 1e-10
+
+
 def test_size_independent_properties_at_full_size(tnsu):
     """Properties that hold at BASELINE's full shape (peps D=8) for any input: weights are positive,
     descending and sum to 1; tensors come back with unit Frobenius norm; RDMs are Hermitian with unit trace;

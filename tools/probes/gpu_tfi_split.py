@@ -10,7 +10,7 @@ smat = tnsu.smc.infinite_structure_matrix_dict("peps")
 pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
 H = (-np.kron(pz, pz) - 3.0 * (np.kron(px, np.eye(2)) + np.kron(np.eye(2), px)) / 4).astype(complex)
 G = linalg.expm(-0.01 * H)
-for B in (1, 256, 2048):
+for B in (256, 4096, 32768):
     eng = tnsu.Engine(smat, 2, [4] * 8, 4, False, batch=B)
     eng.reserve_gate_slots(1)
     eng.set_gates(0, np.broadcast_to(G, (B, 8, 4, 4)))
