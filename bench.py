@@ -289,8 +289,7 @@ def tfi_sweep(n_points, world, rank, local_rank, dist, torch, costs=None):
     energy = batch.energy_per_site()
     mx = batch.expectation_per_site(px)
     mz = batch.expectation_per_site(pz)
-    local = np.stack([energy, mx, mz, np.array([float(lg["converged"]) for lg in logs]),
-                      np.array([float(lg["sweeps"]) for lg in logs])], axis=1)
+    local = np.stack([energy, mx, mz, logs.converged.astype(float), logs.sweeps.astype(float)], axis=1)
     full = sharding.gather_points(local, n_points, world, rank, device=torch.device("cuda", local_rank), costs=costs)
     fused = batch.engine.stats()["fused_runs"]
     torch.cuda.synchronize()
@@ -565,8 +564,8 @@ def run_gpu_arm(args):
         run_energy = sb.energy_per_site()
         barrier()
         whole_s = time.perf_counter() - t0
-        e2e_whole = {"seconds": whole_s, "edges": int(sum(lg["sweeps"] for lg in logs)) * N_E, "n": n_run,
-                     "energy": float(np.mean(run_energy)), "converged": int(sum(lg["converged"] for lg in logs))}
+        e2e_whole = {"seconds": whole_s, "edges": int(logs.sweeps.sum()) * N_E, "n": n_run,
+                     "energy": float(np.mean(run_energy)), "converged": int(logs.converged.sum())}
         sb.engine.close()
 
     # ---- max over ranks ----

@@ -52,6 +52,8 @@ struct EdgeLaunch {
   const EdgeDesc *descs;     // indexed by edge id
   const int *level_edges;    // edge ids handled by this launch
   int n_level_edges;
+  const int *point_list;     // nullptr: launch position = point; else the points this launch covers (batch = its length):
+                             // tnsu_run compacts the points still active so that finished ones cost nothing
   int batch, m_edges, dcap, d4, n_tensors;
   double *weights;           // [batch][m][dcap]
   double *tscale;            // [batch][n_tensors] lazy 1/||T||
@@ -179,8 +181,9 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) lq_kern
   const int rank = CLUSTER ? (int)(blockIdx.x % CL) : 0;
   const int item = (int)(blockIdx.x / CL) >> 1;
   const int side = (int)(blockIdx.x / CL) & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   // behind the streaming CholeskyQR2 kernel (lq_chol.cuh): only the (item, side)s it flagged are factored here
   if (p.lq_flags != nullptr) {
@@ -501,9 +504,10 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   // issue the bulk copy of work item w2's tensor (thread 0 only); returns false when that item is skipped
   auto issue = [&](int w2) {
     const int item2 = w2 >> 1, side2 = w2 & 1;
-    const int b2 = item2 / p.n_level_edges;
+    const int bi2 = item2 / p.n_level_edges;
+    const int b2 = p.point_list != nullptr ? p.point_list[bi2] : bi2;
     if (p.active != nullptr && p.active[b2] == 0) return;
-    const EdgeDesc &ed2 = p.descs[p.level_edges[item2 - b2 * p.n_level_edges]];
+    const EdgeDesc &ed2 = p.descs[p.level_edges[item2 - bi2 * p.n_level_edges]];
     const SideDesc &sd2 = ed2.s[side2];
     const unsigned bytes = (unsigned)((sd2.in_stride_phys * ed2.d * 8 + 15) & ~15LL);
     mbar_expect_tx(bar, bytes);
@@ -526,8 +530,9 @@ __global__ void __launch_bounds__(edge_max_threads<double, MMAX, NCOLS>(), 1) lq
   if (!CLUSTER && p.lq_flags != nullptr && p.lq_flags[w] == 0) continue;  // taken by the streaming kernel: one load per scanned item
   const int item = w >> 1;
   const int side = w & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) {
     if constexpr (STREAM) {
       // nothing was staged for this item; stage the next one now (the buffer is free)
@@ -956,8 +961,9 @@ template <typename S, int RPL>
 __global__ void __launch_bounds__(SVD_THREADS, svd_min_blocks<S, RPL>()) svd_kernel(const EdgeLaunch<S> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int item = blockIdx.x;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   const EdgeDesc &ed = p.descs[ek];
   const SideDesc &si = ed.s[0];
@@ -1312,8 +1318,9 @@ __global__ void __launch_bounds__(edge_max_threads<S, MMAX, NCOLS>(), 1) recompo
   const int rank = (int)(blockIdx.x % CL);
   const int item = (int)(blockIdx.x / CL) >> 1;
   const int side = (int)(blockIdx.x / CL) & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.lq_flags != nullptr && p.lq_flags[blockIdx.x / CL] == 0) return;  // recomposed by recompose_chol_kernel
   const EdgeDesc &ed = p.descs[ek];

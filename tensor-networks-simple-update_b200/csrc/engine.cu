@@ -111,6 +111,8 @@ struct tnsu_engine {
   double *r_log_err = nullptr, *r_log_energy = nullptr;
   int r_log_cap = 0;
   int *h_nactive = nullptr;  // pinned
+  int *d_point_list = nullptr;  // tnsu_run: the points still active, in point order (compacted at the polls)
+  int n_listed = -1;            // its length; -1: launches cover the whole batch
   // failure counters (edge_update.cuh: EdgeLaunch::status) and cumulative statistics (tnsu_stats)
   int *d_status = nullptr;   // [2] device
   int *h_status = nullptr;   // [2] pinned
@@ -529,7 +531,8 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
       p.level_edges = e->d_all_edges + only_edge;
       p.n_level_edges = 1;
     }
-    p.batch = e->batch;
+    p.point_list = (active != nullptr && e->n_listed >= 0) ? e->d_point_list : nullptr;
+    p.batch = p.point_list != nullptr ? e->n_listed : e->batch;
     p.m_edges = e->m;
     p.dcap = e->dcap;
     p.d4 = e->d4;
@@ -578,7 +581,7 @@ static int run_levels(tnsu_engine *e, int fixed_slot, const int *point_slot, con
       p.dbg_info = e->dbg_info;
       p.dbg_point = dbg_point;
     }
-    const int n_items = e->batch * p.n_level_edges;
+    const int n_items = p.batch * p.n_level_edges;
     cudaError_t st = cudaSuccess;
     if (e->profile) cudaEventRecord(e->pev[0], e->stream);
     int extra_launches = 0;
@@ -653,7 +656,8 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
   p.edge_list = edge_list;
   p.first_edge = (edge_list >= e->d_all_edges && edge_list < e->d_all_edges + e->m) ? (int)(edge_list - e->d_all_edges) : -1;
   p.n_list = n_list;
-  p.batch = e->batch;
+  p.point_list = (active != nullptr && e->n_listed >= 0) ? e->d_point_list : nullptr;
+  p.batch = p.point_list != nullptr ? e->n_listed : e->batch;
   p.m_edges = e->m;
   p.dcap = e->dcap;
   p.d4 = e->d4;
@@ -670,7 +674,7 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
       // real path: Gram matrices on the FP64 tensor cores, operands straight from HBM/L2 (rdm.cuh)
       const int MB = (maxM + 7) / 8;
       const int smem_d = pair_dmma_smem_bytes(MB, e->d4);
-      const int grid = e->batch * n_list;
+      const int grid = p.batch * n_list;
       switch (MB) {
         case 1: pair_rdm_dmma_kernel<1><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
         case 2: pair_rdm_dmma_kernel<2><<<grid, PG_THREADS, smem_d, e->stream>>>(p); break;
@@ -685,7 +689,7 @@ static int launch_pair(tnsu_engine *e, const int *edge_list, int n_list, const S
   int smem = pair_smem_bytes(e, maxM);
   if (smem > SMEM_LIMIT) return fail(e, TNSU_E_UNSUPPORTED, "pair RDM needs %d bytes of shared memory", smem);
   CK(tnsu_opt_in_smem((const void *)pair_rdm_kernel<S>));
-  pair_rdm_kernel<S><<<e->batch * n_list, RDM_THREADS, smem, e->stream>>>(p);
+  pair_rdm_kernel<S><<<p.batch * n_list, RDM_THREADS, smem, e->stream>>>(p);
   CK(cudaGetLastError());
   e->launches++;
   return TNSU_OK;
@@ -795,6 +799,35 @@ __global__ void run_state_kernel(RunState s) {
     s.slot[b] = slot;
   }
   atomicAdd(s.nactive, 1);
+}
+
+// Stable compaction of the active points into `list` (one block; the run loop calls it at a poll when points finished):
+// the edge-update and pair-RDM launches that follow cover exactly the listed points, so a finished point costs nothing —
+// with the `active` mask alone its warps return at once, but its CTAs still take part in every launch and leave the
+// CTAs of the remaining points, whose kernels are latency bound, half empty.
+__global__ void compact_active_kernel(const int *active, int n, int *list) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += (int)blockDim.x) {
+    const int i = start + (int)threadIdx.x;
+    const bool a = i < n && active[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) warp_tot[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < w; ++k) off += warp_tot[k];
+    if (a) list[off + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += warp_tot[k];
+      base += t;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void fill_int_kernel(int *p, int n, int v) {
@@ -987,6 +1020,7 @@ int tnsu_destroy(tnsu_engine *e) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (e->h_nactive) cudaFreeHost(e->h_nactive);
+  if (e->d_point_list) cudaFree(e->d_point_list);
   if (e->h_status) cudaFreeHost(e->h_status);
   if (e->d_status) cudaFree(e->d_status);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1612,6 +1646,8 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
   st.edge_err = e->edge_err;
   st.energy = e->energy;
 
+  if (e->d_point_list == nullptr) CK(cudaMalloc(&e->d_point_list, B * sizeof(int)));
+  e->n_listed = -1;
   const long long max_global = (long long)n_dts * max_iterations;
   const int poll = 4;
   bool any = (n_dts > 0 && max_iterations > 0);
@@ -1701,6 +1737,18 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
         break;
       }
       any = (*e->h_nactive > 0);
+      // points finished since the last poll: the launches from here on cover the remaining ones only (a replayed graph
+      // has its grid sizes baked in and keeps the mask)
+      if (any && gexec == nullptr && !e->use_graphs && *e->h_nactive < (e->n_listed >= 0 ? e->n_listed : (int)B)) {
+        compact_active_kernel<<<1, 1024, 0, e->stream>>>(e->r_active, (int)B, e->d_point_list);
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) {
+          rc_loop = fail(e, TNSU_E_CUDA, "run loop compaction: %s", cudaGetErrorString(ce));
+          break;
+        }
+        e->n_listed = *e->h_nactive;
+        e->launches++;
+      }
       // the streaming K1/K3 is only worth its first pass while it keeps most of the bond matrices: when more than half of
       // what it was given since the last poll came back flagged (converged states with small weights), the next 32 sweeps
       // go straight to the Householder kernels, then it is tried again
@@ -1722,6 +1770,7 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
   }
   e->run_sweep_index = 0;
   e->lqc_suspend_until = -1;
+  e->n_listed = -1;
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   if (rc_loop != TNSU_OK) return rc_loop;

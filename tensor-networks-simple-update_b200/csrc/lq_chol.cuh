@@ -261,8 +261,9 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
   const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.lqc_force_fallback == 1) {
     if (threadIdx.x == 0) flags[blockIdx.x] = 1;
@@ -535,8 +536,9 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
   const int n_work = 2 * p.batch * p.n_level_edges;
   if (w >= n_work) return;
   const int item = w >> 1, side = w & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.lqc_force_fallback == 1) {
     if (lane == 0) flags[w] = 1;
@@ -916,8 +918,9 @@ __global__ void __launch_bounds__(RCC_THREADS, (MB <= 2 ? 4 : 2) * (128 / RCC_TH
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, KS = 2 * MB;
   const int item = blockIdx.x >> 1, side = blockIdx.x & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (flags[blockIdx.x] != 0) return;  // the Householder recompose owns this one
   const EdgeDesc &ed = p.descs[ek];

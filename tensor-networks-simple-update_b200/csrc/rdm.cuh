@@ -23,6 +23,7 @@ struct PairRdmLaunch {
   int first_edge;        // >= 0: the list is first_edge, first_edge + 1, ... (saves a dependent global load per CTA)
   int n_list;
   int batch, m_edges, dcap, d4;
+  const int *point_list;         // nullptr, or the points this launch covers (batch = its length)
   const double *weights;
   const S *ops;                  // operator per (point, edge) [batch][m][d4], or one shared op [d4]
   long long op_point_stride;     // 0 when the operator is shared by all points
@@ -36,8 +37,9 @@ struct PairRdmLaunch {
 template <typename S>
 __global__ void __launch_bounds__(RDM_THREADS) pair_rdm_kernel(const PairRdmLaunch<S> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x / p.n_list;
-  const int ek = p.edge_list[blockIdx.x - b * p.n_list];
+  const int bi = blockIdx.x / p.n_list;
+  const int ek = p.edge_list[blockIdx.x - bi * p.n_list];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.iter_state != nullptr) {
     const int it = p.iter_state[b];
@@ -238,8 +240,9 @@ __global__ void __launch_bounds__(PG_THREADS, (MB <= 2 ? 4 : 2) * (256 / PG_THRE
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB;
   constexpr int NBLK = MB * (MB + 1) / 2;
-  const int b = blockIdx.x / p.n_list;
-  const int ek = p.first_edge >= 0 ? p.first_edge + (int)(blockIdx.x - b * p.n_list) : p.edge_list[blockIdx.x - b * p.n_list];
+  const int bi = blockIdx.x / p.n_list;
+  const int ek = p.first_edge >= 0 ? p.first_edge + (int)(blockIdx.x - bi * p.n_list) : p.edge_list[blockIdx.x - bi * p.n_list];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   const int ek_first = p.first_edge >= 0 ? p.first_edge : p.edge_list[0];
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.iter_state != nullptr) {

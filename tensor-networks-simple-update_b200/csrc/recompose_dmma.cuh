@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(RCD_THREADS, (MBO * KB <= 4) ? 4 : 3) recompos
   const int rank = (int)(blockIdx.x % CL);
   const int item = (int)(blockIdx.x / CL) >> 1;
   const int side = (int)(blockIdx.x / CL) & 1;
-  const int b = item / p.n_level_edges;
-  const int ek = p.level_edges[item - b * p.n_level_edges];
+  const int bi = item / p.n_level_edges;  // position in the launch; the point it stands for comes from the list of active points
+  const int ek = p.level_edges[item - bi * p.n_level_edges];
+  const int b = p.point_list != nullptr ? p.point_list[bi] : bi;
   if (p.active != nullptr && p.active[b] == 0) return;
   if (p.lq_flags != nullptr && p.lq_flags[blockIdx.x / CL] == 0) return;  // recomposed by recompose_chol_kernel
   const EdgeDesc &ed = p.descs[ek];

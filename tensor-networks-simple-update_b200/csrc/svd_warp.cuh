@@ -842,8 +842,9 @@ __global__ void __launch_bounds__(SVDW_THREADS, (128 / SVDW_THREADS) * (ACCV ? (
   bool valid = (grp < gpw) && (item < n_items);
   int b = 0, ek = 0;
   if (valid) {
-    b = item / p.n_level_edges;
-    ek = p.level_edges[item - b * p.n_level_edges];
+    const int bi = item / p.n_level_edges;
+    ek = p.level_edges[item - bi * p.n_level_edges];
+    b = p.point_list != nullptr ? p.point_list[bi] : bi;
     if (p.active != nullptr && p.active[b] == 0) valid = false;
   }
   // whole-warp early out (no group of this warp has work)

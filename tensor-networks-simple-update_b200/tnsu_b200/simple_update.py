@@ -13,6 +13,8 @@ independent points (fields, couplings, angles, seeds) of one lattice advance in 
 """
 from __future__ import annotations
 
+from collections.abc import Sequence
+
 import numpy as np
 from scipy import linalg
 
@@ -53,6 +55,50 @@ class _PerPoint:
 
 def per_point(items) -> _PerPoint:
     return _PerPoint(items)
+
+
+class _RunLogs(Sequence):
+    """The per-point logger dicts of a batch run — keys error / dt / iteration / energy (the reference's logger lists,
+    :143-150) plus converged / sweeps / final_dt — built from the downloaded log arrays when a point is looked at: a
+    sweep of tens of thousands of points whose caller reads two scalars per point does not pay for 4 Python lists each."""
+
+    def __init__(self, res, dts):
+        self._res, self._dts = res, dts
+        self._made = [None] * len(dts)
+
+    def __len__(self):
+        return len(self._made)
+
+    def __getitem__(self, p):
+        if isinstance(p, slice):
+            return [self[i] for i in range(*p.indices(len(self)))]
+        if p < 0:
+            p += len(self)
+        if not 0 <= p < len(self):
+            raise IndexError("point index out of range")
+        lg = self._made[p]
+        if lg is None:
+            res, dts = self._res, self._dts[p]
+            k = int(res["n_checks"][p])
+            lg = self._made[p] = {
+                "error": res["log_error"][p, :k].tolist(),
+                "dt": [dts[s] for s in res["log_slot"][p, :k].tolist()],
+                "iteration": res["log_step"][p, :k].tolist(),
+                "energy": res["log_energy"][p, :k].tolist(),
+                "converged": bool(res["converged"][p]),
+                "sweeps": int(res["sweeps"][p]),
+                "final_dt": dts[int(res["final_slot"][p])],
+            }
+        return lg
+
+    @property
+    def sweeps(self) -> np.ndarray:
+        """sweeps every point ran, as one array"""
+        return np.asarray(self._res["sweeps"])
+
+    @property
+    def converged(self) -> np.ndarray:
+        return np.asarray(self._res["converged"]).astype(bool)
 
 
 class SimpleUpdateBatch:
@@ -124,6 +170,12 @@ class SimpleUpdateBatch:
 
     def _params_key(self):
         """Value key of everything the per-edge Hamiltonians depend on (operators by identity)."""
+        if all(h is None for h in self.hamiltonian):
+            try:  # the common case in one go: couplings and fields as bytes
+                values = (np.asarray(self.j_ij, dtype=complex).tobytes(), np.asarray(self.h_k, dtype=complex).tobytes())
+            except (TypeError, ValueError):
+                values = (tuple(tuple(complex(x) for x in j) for j in self.j_ij), tuple(complex(h) for h in self.h_k))
+            return (None, values, tuple(id(a) for a in self.s_i), tuple(id(a) for a in self.s_j), tuple(id(a) for a in self.s_k))
         return (tuple(id(h) for h in self.hamiltonian),
                 tuple(tuple(complex(x) for x in j) if h is None else () for j, h in zip(self.j_ij, self.hamiltonian)),
                 tuple(complex(h) for h in self.h_k),
@@ -167,25 +219,39 @@ class SimpleUpdateBatch:
                 out[p, :] = np.asarray(self.hamiltonian[p], dtype=complex)
         return out
 
-    def _gates(self, hams, dts_of_point):
-        """expm(-dt H) per (point, edge): the distinct (H, dt) pairs go through ONE stacked scipy.linalg.expm call,
-        which applies the same Pade routine per matrix (bit-identical to the reference's one-matrix calls, :470-473;
-        checked in tests/test_host.py)."""
+    @staticmethod
+    def _distinct_gate_inputs(hams, dts_matrix):
+        """Distinct (H, dt_0 .. dt_{k-1}) rows over all (point, edge) pairs: (first, which) with rows[first][which] ==
+        rows.  dts_matrix: [n_points, k] time steps."""
         n_p, m = hams.shape[:2]
         d2 = hams.shape[-1]
-        dts = np.array([complex(x) for x in dts_of_point])
-        if np.all(dts.imag == 0.0):
-            dts = dts.real
-        # distinct (H, dt) pairs: one row of bytes per (point, edge) = the Hamiltonian followed by its time step
-        rows = np.empty((n_p * m, d2 * d2 + 1), dtype=np.complex128)
-        rows[:, :-1] = hams.reshape(n_p * m, d2 * d2)
-        rows[:, -1] = np.repeat(dts, m)
+        k = dts_matrix.shape[1]
+        rows = np.empty((n_p * m, d2 * d2 + k), dtype=np.complex128)
+        rows[:, :d2 * d2] = hams.reshape(n_p * m, d2 * d2)
+        rows[:, d2 * d2:] = np.repeat(dts_matrix, m, axis=0)
+        rows += 0.0  # -0.0 -> +0.0: equal values, equal bytes
         _, first, which = np.unique(rows.view(np.dtype((np.void, rows.shape[1] * 16))).ravel(), return_index=True,
                                     return_inverse=True)
+        return first, which.reshape(n_p, m)
+
+    @staticmethod
+    def _expm_distinct(hams, dts_of_point, first, which):
+        """expm(-dt H) for the distinct rows only, through ONE stacked scipy.linalg.expm call, which applies the same
+        Pade routine per matrix (bit-identical to the reference's one-matrix calls, :470-473; tests/test_host.py)."""
+        n_p, m = hams.shape[:2]
+        d2 = hams.shape[-1]
+        dts = np.asarray(dts_of_point, dtype=np.complex128)
+        if np.all(dts.imag == 0.0):
+            dts = dts.real
         uniq_h = hams.reshape(n_p * m, d2, d2)[first]
         uniq_dt = np.repeat(dts, m)[first]
-        stack = -uniq_dt[:, None, None] * uniq_h
-        return linalg.expm(stack)[which.reshape(n_p, m)]
+        return linalg.expm(-uniq_dt[:, None, None] * uniq_h)[which]
+
+    def _gates(self, hams, dts_of_point):
+        """expm(-dt H) per (point, edge) for one time step per point."""
+        dts = np.array([complex(x) for x in dts_of_point])
+        first, which = self._distinct_gate_inputs(hams, dts[:, None])
+        return self._expm_distinct(hams, dts, first, which)
 
     # ------------------------------------------------------------------ engine lifecycle
     def _current_dims(self):
@@ -196,8 +262,8 @@ class SimpleUpdateBatch:
         """complex128 engine needed?  The tensors are scanned only when they are about to be (re-)uploaded; while the
         device state is the current one the answer of that scan is reused."""
         if not in_sync or self._state_complex is None:
-            self._state_complex = any(np.iscomplexobj(t) and np.any(np.imag(t) != 0.0)
-                                      for tn in self.tensor_networks for t in tn.tensors)
+            self._state_complex = any((t.dtype.kind == "c" if isinstance(t, np.ndarray) else np.iscomplexobj(t))
+                                      and np.any(np.imag(t) != 0.0) for tn in self.tensor_networks for t in tn.tensors)
         if self._state_complex:
             return True
         for a in extra:
@@ -269,14 +335,17 @@ class SimpleUpdateBatch:
         reference leaves them after an update, :435 + :483)."""
         eng = self._engine
         n, m = self.structure_matrix.shape
+        # one conversion per tensor / edge; a point's entry is its row of that array (a view: per-point storage is
+        # disjoint, in-place edits of one network touch no other)
         for t in range(n):
-            vals = eng.get_tensor(t)
-            for p, tn in enumerate(self.tensor_networks):
-                tn.tensors[t] = np.array(vals[p], dtype=np.complex128)
+            vals = eng.get_tensor(t).astype(np.complex128, copy=False)
+            for tn, row in zip(self.tensor_networks, vals):
+                tn.tensors[t] = row
         for e in range(m):
             vals = eng.get_weights(e)
-            for p, tn in enumerate(self.tensor_networks):
-                tn.weights[e] = np.array(vals[p])
+            for tn, row in zip(self.tensor_networks, vals):
+                tn.weights[e] = row
+        self._state_complex = bool(eng.complex)
         self._mark_synced()
 
     def _set_schedule_gates(self):
@@ -284,8 +353,11 @@ class SimpleUpdateBatch:
         if self._gates_key == key:
             return
         n_dts = len(self.dts[0])
+        # one search for the distinct (Hamiltonian, schedule) rows serves every time step of the schedule
+        dts = np.array([[complex(x) for x in d] for d in self.dts]).reshape(self.n_points, n_dts)
+        first, which = self._distinct_gate_inputs(self._hams, dts)
         for s in range(n_dts):
-            self._engine.set_gates(s, self._gates(self._hams, [d[s] for d in self.dts]))
+            self._engine.set_gates(s, self._expm_distinct(self._hams, dts[:, s], first, which))
         self._gates_key = key
 
     # ------------------------------------------------------------------ public API
@@ -300,7 +372,8 @@ class SimpleUpdateBatch:
         self.download_state()
 
     def run(self):
-        """SimpleUpdate.run() for every point.  Returns a list of per-point logger dicts."""
+        """SimpleUpdate.run() for every point.  Returns the per-point logger dicts as a sequence (`_RunLogs`: indexable,
+        iterable, sliceable like a list; a point's dict is built when it is first looked at)."""
         eng = self._ensure_engine()
         self._set_schedule_gates()
         n_dts = len(self.dts[0])
@@ -308,20 +381,8 @@ class SimpleUpdateBatch:
         is_last = [int(self.dts[0][s] == self.dts[0][-1]) for s in range(n_dts)]
         res = eng.run(is_last, self.max_iterations, self.convergence_error)
         self.download_state()
-        loggers = []
-        for p in range(self.n_points):
-            k = int(res["n_checks"][p])
-            loggers.append({
-                "error": res["log_error"][p, :k].tolist(),
-                "dt": [self.dts[p][s] for s in res["log_slot"][p, :k].tolist()],
-                "iteration": res["log_step"][p, :k].tolist(),
-                "energy": res["log_energy"][p, :k].tolist(),
-                "converged": bool(res["converged"][p]),
-                "sweeps": int(res["sweeps"][p]),
-                "final_dt": self.dts[p][int(res["final_slot"][p])],
-            })
-        self.results = loggers
-        return loggers
+        self.results = _RunLogs(res, [list(d) for d in self.dts])
+        return self.results
 
     def energy_per_site(self) -> np.ndarray:
         return self._ensure_engine().energy()
