@@ -113,6 +113,7 @@ struct tnsu_engine {
   int *h_nactive = nullptr;  // pinned
   int *d_point_list = nullptr;  // tnsu_run: the points still active, in point order (compacted at the polls)
   int n_listed = -1;            // its length; -1: launches cover the whole batch
+  bool compact_active = true;   // TNSU_COMPACT=0: keep whole-batch launches with the active mask (A/B comparisons)
   // failure counters (edge_update.cuh: EdgeLaunch::status) and cumulative statistics (tnsu_stats)
   int *d_status = nullptr;   // [2] device
   int *h_status = nullptr;   // [2] pinned
@@ -1100,6 +1101,8 @@ int tnsu_create(tnsu_engine **out, int n, int m, const int64_t *smat, int d, con
     e->force_householder = env && (std::string(env) == "householder" || std::string(env) == "unrolled");
     e->lqc_force_fallback = env && std::string(env) == "fallback";
     e->lqc_cta_kernel = env && std::string(env) == "cta";
+    env = getenv("TNSU_COMPACT");
+    if (env && std::string(env) == "0") e->compact_active = false;
     env = getenv("TNSU_LQ_MIN_N");
     if (env && atoi(env) > 0) e->lq_stream_min_n = atoi(env);
     env = getenv("TNSU_FUSED");
@@ -1739,7 +1742,7 @@ int tnsu_run(tnsu_engine *e, int n_dts, const int32_t *is_last_value, int max_it
       any = (*e->h_nactive > 0);
       // points finished since the last poll: the launches from here on cover the remaining ones only (a replayed graph
       // has its grid sizes baked in and keeps the mask)
-      if (any && gexec == nullptr && !e->use_graphs && *e->h_nactive < (e->n_listed >= 0 ? e->n_listed : (int)B)) {
+      if (any && e->compact_active && gexec == nullptr && !e->use_graphs && *e->h_nactive < (e->n_listed >= 0 ? e->n_listed : (int)B)) {
         compact_active_kernel<<<1, 1024, 0, e->stream>>>(e->r_active, (int)B, e->d_point_list);
         ce = cudaGetLastError();
         if (ce != cudaSuccess) {

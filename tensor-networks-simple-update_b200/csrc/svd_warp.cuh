@@ -633,65 +633,88 @@ DEV void svdw_body(const SvdwArgs &args) {
         ya[r] *= iy;
       }
     }
-    // w[c'] = sum_c theta[c][c'] u[c] = sum_c th[c*lda + c'] u[c]; each half sums its own c and the partner supplies
-    // the rest; lane half h keeps the theta-column indices c' = h*R + r
-    // (one column at a time, its r~_i written right away, so that A and W never sit in registers together)
-    double wx[R], wy[R];
-    const double *thh = th + (size_t)(h * R) * lda;
-    double *wt = gs + args.tb_off;  // R x ldt, free since the transposition
-    const int ldt_w = args.ldt;
+    // w_j[c'] = sum_c theta[c][c'] u_j[c] = sum_c th[c*lda + c'] u_j[c] for the KEPT columns j only (Dnew of the 2 NP the
+    // processors hold): the u_j go to the dead transpose buffer in rank order, lane gl then owns the output index
+    // c' = gl (, gl + G, ...) of EVERY kept column — one theta element loaded per 8 multiply-adds, 8 independent
+    // accumulators — and the results return to the processor layout (wx / wy of the lanes that hold column j) through
+    // the same buffer.  (Before: every processor computed both of its columns, kept or not: 4x the loads and FMAs at
+    // Dnew = 8 of 32, 9 % of the kernel's stall samples.)  Kept columns are taken SVDW_JB at a time, as many as the
+    // buffer holds next to their results.  A lane's u_j is dead once it sits in the buffer: w_j takes its registers (the
+    // columns that are not kept were zeroed above and stay zero), so A and W never sit in registers together.
+    double *wt = gs + args.tb_off;  // R * ldt + 2 R + 2 doubles, free since the transposition
     double *rt_i = valid ? args.rt_i : nullptr;
     const int n_rowidx = valid ? args.ni : 0;
     // theta-row index (qi, i') of my first row, advanced without divisions
     const int gr0 = h * R;
     const int qi0 = gr0 / d, ip0 = gr0 - qi0 * d;
-#pragma unroll 1
+#pragma unroll
     for (int which = 0; which < 2; ++which) {
-      // the loop body always works on (xa -> wx); the second trip sees the y column through a register swap
-      // rolled over the output row (results pass through the dead transpose buffer): R x 2R FMAs of straight-line
-      // code per column would be a quarter of the kernel's instructions
-#pragma unroll 1
-      for (int r = 0; r < R; ++r) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-        for (int c = 0; c < R; c += 2) {
-          s0 = fma(thh[(size_t)c * lda + r], xa[c], s0);
-          s1 = fma(thh[(size_t)c * lda + R + r], xa[c], s1);
-          s2 = fma(thh[(size_t)(c + 1) * lda + r], xa[c + 1], s2);
-          s3 = fma(thh[(size_t)(c + 1) * lda + R + r], xa[c + 1], s3);
-        }
-        s0 += s2;
-        s1 += s3;
-        const double mine = h ? s1 : s0, other = h ? s0 : s1;
-        const double tot = mine + __shfl_xor_sync(0xffffffffu, other, 1);
-        if (in_group) wt[(size_t)r * ldt_w + gl] = tot;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < R; ++r) wx[r] = wt[(size_t)r * ldt_w + (in_group ? gl : 0)];
-      __syncwarp();
       if (which ? sel_y : sel_x) {
         const int xp = which ? rank_y : rank_x;
         int qi = qi0, ip = ip0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (gr0 + r < n_rowidx) rt_i[(ip * Dnew + xp) * ldm + qi] = xa[r];
+          if (gr0 + r < n_rowidx) rt_i[(ip * Dnew + xp) * ldm + qi] = which ? ya[r] : xa[r];
           if (++ip == d) {
             ip = 0;
             ++qi;
           }
         }
       }
+    }
+    {
+      constexpr int JBMAX = 8;
+      const int jb = max(1, min(JBMAX, (R * args.ldt + 2 * R + 2) / (4 * R)));
+      double *usm = wt;                 // [2R][jb]  u_j[c] of the current batch
+      double *wsm = wt + 2 * R * jb;    // [jb][2R]  w_j[c']
+      const int jall = __reduce_max_sync(0xffffffffu, valid ? Dnew : 0);
+      const bool writer = valid && in_group;
+#pragma unroll 1
+      for (int j0 = 0; j0 < jall; j0 += jb) {
+        const int jn = valid ? max(0, min(jb, Dnew - j0)) : 0;
+        const bool bx = sel_x && rank_x >= j0 && rank_x < j0 + jb, by = sel_y && rank_y >= j0 && rank_y < j0 + jb;
+        if (bx) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double ta = xa[r], tw = wx[r];
-        xa[r] = ya[r];
-        ya[r] = ta;
-        wx[r] = wy[r];
-        wy[r] = tw;
+          for (int r = 0; r < R; ++r) usm[(h * R + r) * jb + (rank_x - j0)] = xa[r];
+        }
+        if (by) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) usm[(h * R + r) * jb + (rank_y - j0)] = ya[r];
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int cp = gl; cp < 2 * R; cp += G) {
+          double acc[JBMAX];
+#pragma unroll
+          for (int j = 0; j < JBMAX; ++j) acc[j] = 0.0;
+          const double *tcol = th + cp;
+#pragma unroll 4
+          for (int c = 0; c < 2 * R; ++c) {
+            const double t = tcol[(size_t)c * lda];
+            const double *uc = usm + c * jb;
+#pragma unroll
+            for (int j = 0; j < JBMAX; ++j)
+              if (j < jn) acc[j] = fma(t, uc[j], acc[j]);
+          }
+          if (writer) {
+#pragma unroll
+            for (int j = 0; j < JBMAX; ++j)
+              if (j < jn) wsm[j * 2 * R + cp] = acc[j];
+          }
+        }
+        __syncwarp();
+        if (bx) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) xa[r] = wsm[(rank_x - j0) * 2 * R + h * R + r];
+        }
+        if (by) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) ya[r] = wsm[(rank_y - j0) * 2 * R + h * R + r];
+        }
+        __syncwarp();
       }
     }
-    // after two swaps xa / ya are back in place and (wx, wy) hold the vectors of (x, y)
+    double(&wx)[R] = xa, (&wy)[R] = ya;  // from here on the registers hold the right vectors of the kept columns
     // a kept column with no direction of its own (sigma = 0, or theta^T u underflows) starts from a fixed dense vector
     {
       double n2x = 0.0, n2y = 0.0;

@@ -14,6 +14,8 @@ ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex
 tail -2 gpurun_out/ncu2.log
 python tools/ncu_summary.py launches gpurun_out/${R}_launches.csv > gpurun_out/${R}_launches.txt
 python tools/ncu_summary.py full gpurun_out/${R}_full.ncu-rep > gpurun_out/${R}_ncu_full_summary.txt
+python tools/ncu_summary.py edge gpurun_out/${R}_ncu_full_summary.txt 4096 | sed "s#gpurun_out/#profiles/#" > gpurun_out/${R}_ncu_edge_update.json
+rm -f gpurun_out/${R}_full.ncu-rep
 CMDC="$CMD --dtype c128 --batch 2048"
 $CMDC > gpurun_out/plain_c.json 2> gpurun_out/plain_c.err && \
 ncu --set full --metrics $EXTRA --clock-control none -k regex:"lq_chol|recompose_chol|svd_kernel" -s 12 -c 3 -o gpurun_out/${R}_full_c128 $CMDC > gpurun_out/ncu3.log 2>&1

@@ -64,8 +64,59 @@ def full(path, pattern=None):
                 print(f"   {k:72s} {r[i]:>18s} {units[i]}")
 
 
+def edge(summary_path, edges_per_launch):
+    """profiles/rNN_ncu_edge_update.json (what bench.py quotes under roofline.ncu / roofline.traffic) from a summary
+    written by `full`: the FIRST launch of each of the three edge-update kernels."""
+    import json
+
+    want = {"lq_chol_warp_kernel": None, "svd_warp_kernel": None, "recompose_chol_kernel": None}
+    cur = None
+    for line in open(summary_path):
+        if line.startswith("== "):
+            cur = next((k for k in want if k in line and want[k] is None), None)
+            if cur:
+                want[cur] = {}
+        elif cur and line.strip():
+            parts = line.split()
+            try:
+                want[cur][parts[0]] = float(parts[1].replace(",", ""))
+            except (ValueError, IndexError):
+                pass
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+
+    # bytes need their units: read them again with the unit column
+    dram_bytes = {k: 0.0 for k in want}
+    cur, seen = None, set()
+    for line in open(summary_path):
+        if line.startswith("== "):
+            cur = next((k for k in want if k in line and k not in seen), None)
+            if cur:
+                seen.add(cur)
+        elif cur and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
+            parts = line.split()
+            dram_bytes[cur] += float(parts[1].replace(",", "")) * scale.get(parts[2], 1.0)
+    get = lambda key: {k: v.get(key) for k, v in want.items() if v}  # noqa: E731
+    out = {
+        "source": f"{summary_path} (ncu --set full + DMMA sub-pipe counters, bench.py --batch {edges_per_launch}, one launch of each "
+                  "kernel of a 1-edge level; tools/gpu_profile_round.sh)",
+        "edges_per_launch_triple": edges_per_launch,
+        "dram_bytes": dram_bytes,
+        "kernel_time_us": get("gpu__time_duration.sum"),
+        "fp64_pipe_pct": get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "dmma_pipe_pct": get("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active"),
+        "dram_throughput_pct": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "l2_hit_pct": get("lts__t_sector_hit_rate.pct"),
+        "dram_bytes_per_edge_update": sum(dram_bytes.values()) / edges_per_launch,
+        "algorithmic_bytes_per_edge_update": 262656,
+    }
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "edge":
+        edge(sys.argv[2], int(sys.argv[3]))
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

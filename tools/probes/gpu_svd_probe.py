@@ -24,6 +24,6 @@ for nsw in (0, 1, 3, 8, 12):
     for pt in range(0, B, 16):
         for edge in (0, 3, 6):
             dbg = eng.debug_edge(0, edge, pt)   # NB: debug_edge UPDATES that edge of every point
-            rows.append((dbg["svd_sweeps"], dbg["phase_cycles"]["theta"], dbg["phase_cycles"]["jacobi"]))
+            rows.append((dbg["svd_sweeps"], dbg["phase_cycles"]["theta"], dbg["phase_cycles"]["jacobi"], dbg["phase_cycles"]["extract"]))
     a = np.array(rows)
-    print(f"after {nsw:2d} sweeps: jacobi sweeps mean {a[:,0].mean():.1f} min {a[:,0].min()} max {a[:,0].max()}  pre-phase cycles {a[:,1].mean():.0f}  jacobi cycles {a[:,2].mean():.0f}")
+    print(f"after {nsw:2d} sweeps: jacobi sweeps mean {a[:,0].mean():.1f} min {a[:,0].min()} max {a[:,0].max()}  pre-phase cycles {a[:,1].mean():.0f}  jacobi cycles {a[:,2].mean():.0f}  extract cycles {a[:,3].mean():.0f}")

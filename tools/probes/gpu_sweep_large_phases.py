@@ -14,6 +14,8 @@ n_points = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 smat = tnsu.smc.infinite_structure_matrix_dict("peps")
 pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
 fields = -np.linspace(0.0, 4.0, n_points)
+if len(sys.argv) > 2 and sys.argv[2] == "shuffled":  # points in random order: finished points are scattered over the batch
+    fields = np.random.default_rng(1).permutation(fields)
 nets = []
 for k in range(n_points):
     np.random.seed(k)
@@ -41,5 +43,6 @@ t5 = time.perf_counter()
 sweeps = np.array([lg["sweeps"] for lg in logs])
 print(f"{n_points} points: ctor {t1 - t0:.3f} s, engine + upload {t2 - t1:.3f}, gates {t3 - t2:.3f}, run() {t4 - t3:.3f}, "
       f"energy + Mx {t5 - t4:.3f}; total {t5 - t0:.3f} s; sweeps max {sweeps.max()} mean {sweeps.mean():.0f}")
-pstats.Stats(pr0).sort_stats("cumulative").print_stats(22)
-pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+if len(sys.argv) > 3:
+    pstats.Stats(pr0).sort_stats("cumulative").print_stats(22)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(3)
