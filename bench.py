@@ -735,7 +735,7 @@ def main():
     ap.add_argument("--converged-networks", type=int, default=1184,
                     help="networks per GPU that run() to convergence for the converged-state headline (tiled over the batch); 0 skips it")
     ap.add_argument("--c128-batch", type=int, default=4096, help="batch of the complex128 sub-measurement; 0 skips it")
-    ap.add_argument("--e2e-run-networks", type=int, default=296, help="networks per GPU of the whole-run end-to-end measurement; 0 skips it")
+    ap.add_argument("--e2e-run-networks", type=int, default=2368, help="networks per GPU of the whole-run end-to-end measurement; 0 skips it")
     ap.add_argument("--dtype", choices=["f64", "c128"], default="f64")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--energy-steps", type=int, default=10)

@@ -84,7 +84,8 @@ DEV bool svdw_rotate(double (&pa)[R], double (&pv)[R], double (&qa)[R], double (
 //   flip = false:  x' = s x + c y,  y' = c x - s y        flip = true:  x' = -s x + c y,  y' = c x + s y
 // where (c, s) come from (al, be, ga) = (|P|^2, |Q|^2, P.Q) of the ordered pair (P, Q) = flip ? (y, x) : (x, y).
 template <int R>
-DEV void svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, int &max_ecos, int &max_esin, bool flip, bool idle, bool exact) {
+DEV void svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, int &max_ecos, int &max_esin, bool flip, bool idle, bool exact,
+                     bool frozen) {
   // nx, ny: the squared norms of the two columns, CARRIED ALONG (both row halves hold the same values): they are
   // updated from the rotation below instead of being recomputed for every pair — two of the three dot products of a
   // step.  The sweep loop refreshes them from the columns once per sweep; `exact` (warp-uniform: an iteration far
@@ -118,7 +119,8 @@ DEV void svdw_step_a(double (&xa)[R], double (&ya)[R], double &nx, double &ny, i
   const double tol2 = 2.25e-30;
   const double g2 = ga * ga;
   const double ab = al * be;
-  const bool rot = !idle && (g2 > tol2 * ab) && (g2 > 0.0);
+  // frozen: this lane's theta has finished while another theta of the warp still iterates — its columns only keep moving
+  const bool rot = !idle && !frozen && (g2 > tol2 * ab) && (g2 > 0.0);
   double c = 1.0, s = 0.0;
   if (rot) {
     const double delta = be - al;
@@ -515,6 +517,12 @@ DEV void svdw_body(const SvdwArgs &args) {
     // to 0.9 sweeps saved per theta, cosines left behind <= 1.6e-15.  Pairs of (nearly) equal singular values rotate by
     // large angles at tiny cosines: they do not pass, and the usual rotation-free sweep confirms them.
     // The test runs on binary exponents: log2(cos^2 sin^2) < max_ecos + max_esin + 2 <= -99 < log2(2.6e-30).
+    // The decision is taken PER THETA (a warp hosts up to four small ones): a finished theta is frozen — its columns keep
+    // moving with the others' but are not rotated any more — so what a point computes does not depend on which other
+    // points share its warp (tests: test_launches_over_the_running_points_only compares bit for bit).
+    const unsigned jall_groups = (gpw * G >= 32) ? 0xffffffffu : ((1u << (gpw * G)) - 1u);
+    const unsigned jmask = in_group ? (G >= 32 ? 0xffffffffu : (((1u << G) - 1u) << base)) : ~jall_groups;
+    bool frozen = !valid;
     int src_pending = lane;
     for (; sweeps < max_sweeps; ++sweeps) {
       int max_ecos = -100000, max_esin = -100000;  // no rotation yet
@@ -546,10 +554,11 @@ DEV void svdw_body(const SvdwArgs &args) {
         for (int r = 0; r < R; ++r) xa[r] = __shfl_sync(0xffffffffu, xa[r], src_pending);
         nx = __shfl_sync(0xffffffffu, nx, src_pending);
         const bool flip = (st & 1) != 0;
-        svdw_step_a<R>(xa, ya, nx, ny, max_ecos, max_esin, flip, flip && last, exact);
+        svdw_step_a<R>(xa, ya, nx, ny, max_ecos, max_esin, flip, flip && last, exact, frozen);
         src_pending = flip ? src_prev : src_next;
       }
-      if (__reduce_max_sync(0xffffffffu, max_ecos) + __reduce_max_sync(0xffffffffu, max_esin) <= -101) {
+      if (__reduce_max_sync(jmask, max_ecos) + __reduce_max_sync(jmask, max_esin) <= -101) frozen = true;
+      if (__all_sync(0xffffffffu, frozen)) {
         ++sweeps;
         jacobi_done = true;
         break;
@@ -597,29 +606,39 @@ DEV void svdw_body(const SvdwArgs &args) {
   }
   const bool sel_x = valid && rank_x < Dnew;
   const bool sel_y = valid && rank_y < Dnew;
+  // sum(s) and the convergence error are summed IN RANK ORDER (through a dead buffer of at least 2 R doubles): which
+  // lane holds which column at the end depends on how many sweeps the warp ran — with several small thetas per warp on
+  // the slowest of them — and sums in lane order would make a point's last bits depend on its neighbours in the batch
+  double *rs = ACCV ? th : gs + args.tb_off;  // ACCV: theta is dead; V-free: the transpose buffer, free until the recovery
+  const int dn = valid ? Dnew : 0;
+  if (sel_x && h == 0) rs[rank_x] = sx;
+  if (sel_y && h == 0) rs[rank_y] = sy;
+  __syncwarp();
   double tot = 0.0;
-  {
-    const double mine = (sel_x ? sx : 0.0) + (sel_y ? sy : 0.0);
-    for (int j = 0; j < NP; ++j) tot += __shfl_sync(0xffffffffu, mine, in_group ? base + 2 * j : lane);
-  }
+  for (int r = 0; r < dn; ++r) tot += rs[r];
+  __syncwarp();
   if (valid && gl == 0 && !(tot > 0.0 && tot < 1e300)) atomicOr(args.status, 1);  // NaN / Inf in the state (or theta == 0)
   if (!jacobi_done && lane == 0) atomicAdd(args.status + 1, 1);
   // lambda' = s / sum(s)  (reference :296) and this edge's convergence error (:196-206)
-  double e2 = 0.0;
   if (sel_x) {
     const double ln = sx / tot;
-    if (h == 0) lamv[rank_x] = ln;
     const double df = ln - lam_old[rank_x];
-    e2 += df * df;
+    if (h == 0) {
+      lamv[rank_x] = ln;
+      rs[rank_x] = df * df;
+    }
   }
   if (sel_y) {
     const double ln = sy / tot;
-    if (h == 0) lamv[rank_y] = ln;
     const double df = ln - lam_old[rank_y];
-    e2 += df * df;
+    if (h == 0) {
+      lamv[rank_y] = ln;
+      rs[rank_y] = df * df;
+    }
   }
+  __syncwarp();
   double err2 = 0.0;
-  for (int j = 0; j < NP; ++j) err2 += __shfl_sync(0xffffffffu, e2, in_group ? base + 2 * j : lane);
+  for (int r = 0; r < dn; ++r) err2 += rs[r];
   if (valid && gl == 0) *args.edge_err = (Dnew == Dk) ? sqrt(err2) : nan("");
 
   if constexpr (!ACCV) {

@@ -456,6 +456,37 @@ def test_narrow_bond_matrices_stream_once_the_batch_fills_the_gpu(tnsu, monkeypa
         assert abs(orc.energy_per_site(t, w, smat, model) - e_big[j]) < 1e-10
 
 
+def test_launches_over_the_running_points_only(tnsu, monkeypatch):
+    """tnsu_run compacts the points still running at its polls and launches over that list (EdgeLaunch::point_list); with
+    TNSU_COMPACT=0 it keeps whole-batch launches with the active mask.  Points of one batch finish after 6 to 60 sweeps
+    here; both ways give the same checks, logs, weights and energies — a point's arithmetic does not depend on where in
+    a launch it sits — and the list needs fewer launches' worth of work (same launch count + the compactions)."""
+    pz, px = np.array([[1, 0], [0, -1]]), np.array([[0, 1], [1, 0]])
+    smat = tnsu.smc.infinite_structure_matrix_dict("peps")
+    fields = [-0.2 - 0.1 * k for k in range(40)]
+    out = {}
+    monkeypatch.setenv("TNSU_FUSED", "0")
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TNSU_COMPACT", mode)
+        nets = []
+        for k in range(len(fields)):
+            np.random.seed(500 + k)
+            nets.append(tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=2, spin_dim=2))
+        b = tnsu.SimpleUpdateBatch(nets, [-1.0] * 8, tnsu.per_point(fields), [pz], [pz], [px], [0.1, 0.01], d_max=3,
+                                   max_iterations=30, convergence_error=1e-6)
+        logs = b.run()
+        out[mode] = (logs, b.energy_per_site(), [np.array(w) for tn in nets for w in tn.weights], b.engine.stats()["launches"])
+    a, c = out["1"], out["0"]
+    assert len({lg["sweeps"] for lg in a[0]}) > 3  # the points do finish at different times
+    for la, lc in zip(a[0], c[0]):
+        assert la["iteration"] == lc["iteration"] and la["converged"] == lc["converged"] and la["sweeps"] == lc["sweeps"]
+        assert np.array_equal(np.array(la["error"]), np.array(lc["error"]))
+        assert np.array_equal(np.array(la["energy"]), np.array(lc["energy"]))
+    assert np.array_equal(a[1], c[1])
+    assert all(np.array_equal(x, y) for x, y in zip(a[2], c[2]))
+    assert a[3] > c[3]  # the compaction launches themselves
+
+
 def test_size_independent_properties_at_full_size(tnsu):
     """Properties that hold at BASELINE's full shape (peps D=8) for any input: weights are positive,
     descending and sum to 1; tensors come back with unit Frobenius norm; RDMs are Hermitian with unit trace;
