@@ -513,10 +513,20 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
 #define LQW_CHUNK 128
 #define LQW_WL 16
 
-static inline int lqw_smem_bytes_per_warp(int MB) {
+// complex128 keeps L1 as a packed complex matrix (MP^2 / 2 doubles) instead of an MP x (MP + 1) real one, and its packed
+// L2 / W2 take the place of the Gram matrix once that sits in registers
+static inline int lqw_smem_bytes_per_warp(int MB, bool cx = false) {
   const int MP = 8 * MB;
-  return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + 4 * MP * (MP + 1) * 8 + 160 * 8 + 16;
+  const int mats = cx ? 2 * MP * (MP + 1) + MP * MP / 2 : 4 * MP * (MP + 1);
+  return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + mats * 8 + 160 * 8 + 16;
 }
+// Warps (= independent factorisations) per CTA.  The wide complex128 variants need 30 KB of shared memory and > 200
+// registers per warp: one-warp CTAs let the SM take as many as fit (8 instead of the 4 of one four-warp CTA).
+template <int MB, bool CX>
+struct LqwCfg {
+  static constexpr int warps = (CX && MB > 2) ? 1 : LQW_WARPS;
+  static constexpr int min_blocks = (CX && MB > 2) ? 8 : (MB <= 2 ? 4 : 2);
+};
 
 // CX = true: complex128.  The bond matrix is handled as the REAL matrix of its row-interleaved parts (row 2r = Re P[r],
 // row 2r + 1 = Im P[r]: the (re, im) pairs of the tensor storage, 8 bytes apart): its 2M x 2M real Gram holds the four
@@ -525,14 +535,14 @@ static inline int lqw_smem_bytes_per_warp(int MB) {
 // inverse steps and the final L = L1 L2, L^-1 = W2 W1 are done in complex arithmetic.  MB counts 8-row blocks of the real
 // rows (2M <= 8 MB).
 template <int MB, bool CX>
-__global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
+__global__ void __launch_bounds__(32 * LqwCfg<MB, CX>::warps, LqwCfg<MB, CX>::min_blocks)
     lq_chol_warp_kernel(const EdgeLaunch<typename std::conditional<CX, cplx, double>::type> p, int *flags, int smem_per_warp) {
   typedef typename std::conditional<CX, cplx, double>::type S;
   constexpr int ESZ = CX ? 16 : 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int MP = 8 * MB, LD = MP + 1, NBLK = MB * (MB + 1) / 2, KS = 2 * MB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int w = blockIdx.x * LQW_WARPS + warp;  // work item = (item, side)
+  const int w = blockIdx.x * LqwCfg<MB, CX>::warps + warp;  // work item = (item, side)
   const int n_work = 2 * p.batch * p.n_level_edges;
   if (w >= n_work) return;
   const int item = w >> 1, side = w & 1;
@@ -555,8 +565,8 @@ __global__ void __launch_bounds__(32 * LQW_WARPS, MB <= 2 ? 4 : 2)
   LqcLeg *legs = (LqcLeg *)(cols + LQW_CHUNK);
   double *wl = (double *)(legs + TNSU_MAX_LEGS);      // [legs][LQW_WL]
   double *G = wl + TNSU_MAX_LEGS * LQW_WL;            // Gram matrix of the current pass, later L2
-  double *L1s = G + MP * LD, *W1s = L1s + MP * LD, *W2s = W1s + MP * LD;
-  double *scr = W2s + MP * LD;   // [128] column broadcast of the Cholesky steps
+  double *L1s = G + MP * LD, *W1s = L1s + (CX ? MP * MP / 2 : MP * LD), *W2s = CX ? G : W1s + MP * LD;
+  double *scr = W1s + (CX ? 1 : 2) * MP * LD;   // [128] column broadcast of the Cholesky steps
   double *dinv = scr + 128;      // [32] reciprocal diagonal of the current Cholesky factor
 
   const double *wpoint = p.weights + (size_t)b * p.m_edges * p.dcap;
@@ -1126,7 +1136,8 @@ cudaError_t launch_lq_chol_v(const EdgeLaunch<double> &p, int n_items, int *flag
     auto kw = lq_chol_warp_kernel<MB, false>;
     if (cudaError_t s = tnsu_opt_in_smem((const void *)kw); s != cudaSuccess) return s;
     const int per_warp = lqw_smem_bytes_per_warp(MB);
-    kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
+    constexpr int NW = LqwCfg<MB, false>::warps;
+    kw<<<(2 * n_items + NW - 1) / NW, 32 * NW, per_warp * NW, st>>>(p, flags, per_warp);
     return cudaGetLastError();
   }
   kern<<<2 * n_items, LQC_THREADS, lqc_smem_bytes(MB), st>>>(p, flags);
@@ -1144,8 +1155,9 @@ template <int MB>
 cudaError_t launch_lq_chol_cx_v(const EdgeLaunch<cplx> &p, int n_items, int *flags, cudaStream_t st) {
   auto kw = lq_chol_warp_kernel<MB, true>;
   if (cudaError_t s = tnsu_opt_in_smem((const void *)kw); s != cudaSuccess) return s;
-  const int per_warp = lqw_smem_bytes_per_warp(MB);
-  kw<<<(2 * n_items + LQW_WARPS - 1) / LQW_WARPS, 32 * LQW_WARPS, per_warp * LQW_WARPS, st>>>(p, flags, per_warp);
+  const int per_warp = lqw_smem_bytes_per_warp(MB, true);
+  constexpr int NW = LqwCfg<MB, true>::warps;
+  kw<<<(2 * n_items + NW - 1) / NW, 32 * NW, per_warp * NW, st>>>(p, flags, per_warp);
   return cudaGetLastError();
 }
 template <int MB>
