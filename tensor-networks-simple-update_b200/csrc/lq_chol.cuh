@@ -520,12 +520,13 @@ static inline int lqw_smem_bytes_per_warp(int MB, bool cx = false) {
   const int mats = cx ? 2 * MP * (MP + 1) + MP * MP / 2 : 4 * MP * (MP + 1);
   return LQW_CHUNK * 16 + TNSU_MAX_LEGS * 16 + TNSU_MAX_LEGS * LQW_WL * 8 + mats * 8 + 160 * 8 + 16;
 }
-// Warps (= independent factorisations) per CTA.  The wide complex128 variants need 30 KB of shared memory and > 200
-// registers per warp: one-warp CTAs let the SM take as many as fit (8 instead of the 4 of one four-warp CTA).
+// Warps (= independent factorisations) per CTA.  The wide variants (more than 16 real rows: complex128 at d D > 8, real
+// at d D > 16) need 25-38 KB of shared memory and > 200 registers per warp: one-warp CTAs let the SM take as many as fit
+// (8 complex / 5 real instead of the 4 of one four-warp CTA).
 template <int MB, bool CX>
 struct LqwCfg {
-  static constexpr int warps = (CX && MB > 2) ? 1 : LQW_WARPS;
-  static constexpr int min_blocks = (CX && MB > 2) ? 8 : (MB <= 2 ? 4 : 2);
+  static constexpr int warps = (MB > 2) ? 1 : LQW_WARPS;
+  static constexpr int min_blocks = (MB > 2) ? (CX ? 8 : 5) : 4;
 };
 
 // CX = true: complex128.  The bond matrix is handled as the REAL matrix of its row-interleaved parts (row 2r = Re P[r],
