@@ -863,8 +863,17 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
   const double tol2 = 2.25e-30;  // (1.5e-15)^2
   int sweeps = 0;
   __syncthreads();
+  // flag[0]: a rotation happened in this sweep; flag[2], flag[3]: the largest binary exponents of cos^2 of a pair met
+  // and of |sin|^2 of a rotation applied.  As in the warp kernel (svd_warp.cuh) the iteration also ends after a sweep
+  // whose (max cosine) x (max |sin|) is below 7.9e-16: the cosines such a sweep leaves behind are <= 2 (n - 1) times
+  // that, 1e-13 at n = 64, and the confirming sweep would only establish it.
+  int *iflag = const_cast<int *>(flag);
   for (; sweeps < max_sweeps; ++sweeps) {
-    if (tid == 0) *flag = 0;
+    if (tid == 0) {
+      flag[0] = 0;
+      flag[2] = -100000;
+      flag[3] = -100000;
+    }
     __syncthreads();
     for (int r = 0; r < nm1; ++r) {
       for (int pp = group; pp < npairs; pp += ngroups) {
@@ -936,13 +945,17 @@ __device__ int jacobi_svd(S *A, int lda, int nr, int nc, S *V, int ldv, volatile
                 }
               }
             }
-            if (lane8 == 0) *flag = 1;
+            if (lane8 == 0) {
+              flag[0] = 1;
+              atomicMax(iflag + 2, ((__double2hiint(g2) >> 20) & 0x7ff) - ((__double2hiint(al * be) >> 20) & 0x7ff));
+              atomicMax(iflag + 3, ((__double2hiint(abs2(sq)) >> 20) & 0x7ff) - 1023);
+            }
           }
         }
       }
       __syncthreads();
     }
-    if (*flag == 0) return sweeps + 1;
+    if (flag[0] == 0 || flag[2] + flag[3] <= -103) return sweeps + 1;
     __syncthreads();  // everyone has read the flag before the next sweep resets it
   }
   return 99;  // sweep limit reached without a rotation-free sweep
