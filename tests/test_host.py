@@ -176,3 +176,56 @@ def test_stacked_expm_is_bit_identical_to_single_calls():
     for stack in (hams, herm):
         for dt in (0.1, 0.001, 0.05j):
             assert np.array_equal(linalg.expm(-dt * stack), np.array([linalg.expm(-dt * h) for h in stack]))
+
+
+def test_schedule_gates_are_deduplicated_once_and_bit_identical():
+    """_set_schedule_gates searches the distinct (Hamiltonian, dt schedule) rows ONCE for all time steps and
+    exponentiates only those; every (point, edge, step) gate must equal the reference's one-matrix call
+    expm(-dt H) (simple_update.py:470-473) bit for bit — shared and per-point schedules, repeated Hamiltonians, -0.0."""
+    from scipy import linalg
+    from tnsu_b200.simple_update import SimpleUpdateBatch
+
+    pz, px = np.array([[1.0, 0], [0, -1.0]]), np.array([[0, 1.0], [1.0, 0]])
+    fields = [-0.5, -2.0, -0.5, 0.0, -0.0, -3.0]  # points 0 / 2 and 3 / 4 share their Hamiltonians
+    n_p, m = len(fields), 3
+    hams = np.empty((n_p, m, 4, 4), dtype=complex)
+    for p, h in enumerate(fields):
+        for e in range(m):
+            hams[p, e] = -np.kron(pz, pz) + h * (np.kron(px, np.eye(2)) / (2 + e % 2) + np.kron(np.eye(2), px) / 4)
+    for dts in (np.tile([0.1, 0.01, 0.001], (n_p, 1)).astype(complex),
+                np.array([[0.1, 0.01, 0.001], [0.2, 0.01, 0.001], [0.1, 0.01, 0.001], [0.1, 0.05j, 0.001], [0.1, 0.05j, 0.001],
+                          [0.3, 0.02, 0.002]], dtype=complex)):
+        first, which = SimpleUpdateBatch._distinct_gate_inputs(hams, dts)
+        assert len(first) < n_p * m  # something was shared
+        for s in range(dts.shape[1]):
+            gates = SimpleUpdateBatch._expm_distinct(hams, dts[:, s], first, which)
+            assert gates.shape == (n_p, m, 4, 4)
+            for p in range(n_p):
+                dt = dts[p, s].real if np.all(dts[:, s].imag == 0) else dts[p, s]
+                for e in range(m):
+                    assert np.array_equal(gates[p, e], linalg.expm(-dt * hams[p, e]))
+
+
+def test_run_logs_sequence():
+    """SimpleUpdateBatch.run() hands back the per-point logger dicts as a lazy sequence: list semantics (len, index,
+    negative index, slice, iteration), the reference's logger keys per point, arrays for whole-batch reads."""
+    from tnsu_b200.simple_update import _RunLogs
+
+    n, cap = 5, 4
+    res = dict(n_checks=np.array([2, 0, 4, 1, 3], dtype=np.int32),
+               log_error=np.arange(n * cap, dtype=float).reshape(n, cap) / 1024.0,
+               log_energy=-np.arange(n * cap, dtype=float).reshape(n, cap),
+               log_slot=np.tile(np.array([0, 0, 1, 1], dtype=np.int32), (n, 1)),
+               log_step=np.tile(np.array([3, 5, 7, 9], dtype=np.int32), (n, 1)),
+               converged=np.array([1, 0, 1, 0, 1], dtype=np.int32), sweeps=np.array([5, 2, 9, 3, 7], dtype=np.int32),
+               final_slot=np.array([1, 0, 1, 0, 1], dtype=np.int32))
+    logs = _RunLogs(res, [[0.1, 0.01]] * n)
+    assert len(logs) == n and [lg["sweeps"] for lg in logs] == [5, 2, 9, 3, 7]
+    assert logs[0] is logs[0] and logs[-1]["sweeps"] == 7 and [lg["sweeps"] for lg in logs[1:3]] == [2, 9]
+    assert logs[2]["error"] == [8 / 1024, 9 / 1024, 10 / 1024, 11 / 1024] and logs[2]["dt"] == [0.1, 0.1, 0.01, 0.01]
+    assert logs[2]["iteration"] == [3, 5, 7, 9] and logs[2]["energy"] == [-8.0, -9.0, -10.0, -11.0]
+    assert logs[1]["error"] == [] and logs[1]["converged"] is False and logs[1]["final_dt"] == 0.1
+    assert logs[4]["converged"] is True and logs[4]["final_dt"] == 0.01
+    assert np.array_equal(logs.sweeps, res["sweeps"]) and logs.converged.tolist() == [True, False, True, False, True]
+    with pytest.raises(IndexError):
+        logs[n]
