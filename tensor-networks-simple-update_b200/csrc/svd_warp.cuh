@@ -17,8 +17,11 @@
 // of step B (positions n-1 and 0, sitting together in the last processor) gets the "rotation" (c,s)=(0,1),
 // which keeps both in place (one changes sign together with its V column: harmless).
 //
-// Cost per step and lane at R = 16: 64 SHFL + ~210 FP64 instructions -> FP64-pipe bound (measured B200
-// rates: 1 warp-SHFL / clk / SM, 1 warp-DFMA / 2 clk / SM sub-partition; profiles/r01_microbench_b200.txt).
+// Cost per half step and lane at R = 16: 64 SHFL + ~210 FP64 instructions with the accumulator (ACCV); the default
+// V-free iteration with carried column norms: 38 SHFL + 117 FP64 of ~290 instructions (measured B200 rates: 1 warp-SHFL
+// / clk / SM, 1 warp-DFMA / 2 clk / SM sub-partition; profiles/r01_microbench_b200.txt).  Under load the kernel follows
+// the dependent chain of a step (dot -> shuffle -> two rsqrt -> update -> shift) times the 4 warps a scheduler holds, not
+// the instruction count: profiles/r02_k2_stall_lines.txt, DESIGN.md section 4.
 #pragma once
 #include "edge_update.cuh"
 
