@@ -510,6 +510,9 @@ __global__ void __launch_bounds__(LQC_THREADS, MB <= 2 ? 10 : 4) lq_chol_kernel(
 // are four independent factorisations whose serial phases hide behind each other's DMMAs
 // =================================================================================================================
 #define LQW_WARPS 4
+#ifndef LQW_MB1_BLOCKS
+#define LQW_MB1_BLOCKS 8
+#endif
 #define LQW_CHUNK 128
 #define LQW_WL 16
 
@@ -526,7 +529,7 @@ static inline int lqw_smem_bytes_per_warp(int MB, bool cx = false) {
 template <int MB, bool CX>
 struct LqwCfg {
   static constexpr int warps = (MB > 2) ? 1 : LQW_WARPS;
-  static constexpr int min_blocks = (MB > 2) ? (CX ? 8 : 5) : 4;
+  static constexpr int min_blocks = (MB > 2) ? (CX ? 8 : 5) : ((MB == 1 && !CX) ? LQW_MB1_BLOCKS : 4);
 };
 
 // CX = true: complex128.  The bond matrix is handled as the REAL matrix of its row-interleaved parts (row 2r = Re P[r],
