@@ -456,12 +456,16 @@ def test_narrow_bond_matrices_stream_once_the_batch_fills_the_gpu(tnsu, monkeypa
         assert abs(orc.energy_per_site(t, w, smat, model) - e_big[j]) < 1e-10
 
 
-def test_launches_over_the_running_points_only(tnsu, monkeypatch):
+@pytest.mark.parametrize("complex_field", [False, True])
+def test_launches_over_the_running_points_only(tnsu, monkeypatch, complex_field):
     """tnsu_run compacts the points still running at its polls and launches over that list (EdgeLaunch::point_list); with
     TNSU_COMPACT=0 it keeps whole-batch launches with the active mask.  Points of one batch finish after 6 to 60 sweeps
     here; both ways give the same checks, logs, weights and energies — a point's arithmetic does not depend on where in
-    a launch it sits — and the list needs fewer launches' worth of work (same launch count + the compactions)."""
+    a launch it sits — and the list needs fewer launches' worth of work (same launch count + the compactions).
+    complex_field: a Sy field term makes the gates complex, i.e. the same through the complex128 kernels."""
     pz, px = np.array([[1, 0], [0, -1]]), np.array([[0, 1], [1, 0]])
+    if complex_field:
+        px = np.array([[0, -1j], [1j, 0]])
     smat = tnsu.smc.infinite_structure_matrix_dict("peps")
     fields = [-0.2 - 0.1 * k for k in range(40)]
     out = {}
