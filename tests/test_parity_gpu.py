@@ -255,6 +255,52 @@ def test_large_shapes_match_oracle(tnsu, lattice, dim, d, cplx_init):
     assert abs(su.energy_per_site() - e_ref) < TOL_E * max(1.0, abs(e_ref))
 
 
+def test_randomized_cases_match_oracle(tnsu):
+    """30 seeded random cases — lattice (chain, star, peps, triangle, cube), d in {2, 3}, bond dimension with growth,
+    couplings of mixed sign, an Sx or Sy (complex gates) field of random strength, dt, real or complex initial tensors —
+    three sweeps each against the oracle on the same input: weights and energy within 1e-10 (measured <= 6e-15).  Shapes
+    beyond the build's limits are refused loudly, never computed differently."""
+    rng = np.random.default_rng(7)
+    lattices = {"chain": (2, 12), "star": (2, 8), "peps": (2, 8), "triangle": (2, 3), "cube": (2, 3)}
+    ran = refused = 0
+    for case in range(30):
+        name = list(lattices)[rng.integers(len(lattices))]
+        lo, hi = lattices[name]
+        d = int(rng.choice([2, 2, 3]))
+        hi = max(lo, min(hi, 32 // d))
+        dim0 = int(rng.integers(lo, hi + 1))
+        d_max = int(rng.integers(dim0, min(hi, dim0 + 3) + 1))
+        smat = tnsu.smc.infinite_structure_matrix_dict(name)
+        m = smat.shape[1]
+        sx, sy, sz = tnsu.spin_operators((d - 1) / 2.0)
+        use_sy, cplx_init = bool(rng.integers(4) == 0), bool(rng.integers(5) == 0)
+        field, dt = float(rng.normal()), float(rng.choice([0.1, 0.03, 0.005]))
+        s_k = [sy] if use_sy else [sx]
+        j = [float(x) for x in rng.choice([-1.0, 1.0, 0.5], size=m)]
+        np.random.seed(1000 + case)
+        tn = tnsu.TensorNetwork(structure_matrix=smat, virtual_dim=dim0, spin_dim=d)
+        if cplx_init:
+            tn.tensors = [t + 1j * np.random.normal(size=t.shape) for t in tn.tensors]
+        t_ref, w_ref = [np.array(t) for t in tn.tensors], [np.array(w) for w in tn.weights]
+        su = tnsu.SimpleUpdate(tn, j, field, [sx, sy, sz], [sx, sy, sz], s_k, [dt], d_max=d_max, print_process=False)
+        su.dt = dt
+        model = orc.Model(j, field, [sx, sy, sz], [sx, sy, sz], s_k)
+        try:
+            for _ in range(3):
+                su.simple_update()
+        except tnsu.EngineError as exc:
+            assert "UNSUPPORTED" in str(exc)
+            refused += 1
+            continue
+        for _ in range(3):
+            orc.sweep(t_ref, w_ref, smat, model, dt, d_max)
+        ran += 1
+        assert max(np.abs(a - b).max() for a, b in zip(w_ref, tn.weights)) < TOL_W, (case, name, d, dim0, d_max)
+        e_ref = orc.energy_per_site(t_ref, w_ref, smat, model)
+        assert abs(su.energy_per_site() - e_ref) < TOL_E * max(1.0, abs(e_ref)), (case, name, d, dim0, d_max)
+    assert ran >= 25 and refused <= 5
+
+
 def test_unsupported_shapes_fail_loudly(tnsu):
     """Beyond the on-chip limits the engine refuses (TNSU_E_UNSUPPORTED) instead of falling back to anything."""
     smat = tnsu.smc.infinite_structure_matrix_dict("triangle")
